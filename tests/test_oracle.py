@@ -1,0 +1,125 @@
+"""The CPU oracle (oracle/tsb_oracle.c) against the committed golden vectors produced by the
+reference's own C sources (tests/golden/make_golden.py) and the counts its binaries print."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+INT_MAX = 2**31 - 1
+
+
+@pytest.fixture(scope="module")
+def counts(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "counts.json")))
+
+
+@pytest.fixture(scope="module")
+def nq_gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "nqueens_labels.npz"))
+
+
+@pytest.fixture(scope="module")
+def pf_gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "pfsp_bounds.npz"))
+
+
+@pytest.mark.parametrize("N", [5, 8, 14, 17, 19, 20])
+def test_nq_labels_match_reference_isSafe(nq_gold, N):
+    parents = nq_gold[f"parents_N{N}"].view(po.NQ_NODE_DTYPE)
+    want = nq_gold[f"labels_N{N}"]
+    for g in (1, 3):
+        got = po.nq_evaluate(parents, N, g)
+        np.testing.assert_array_equal(got, want)  # includes the untouched (0xCD) slots k < depth
+
+
+@pytest.mark.parametrize("inst", [1, 14, 20, 21])
+def test_tables_match_reference(pf_gold, inst):
+    tag = f"ta{inst:03d}"
+    jobs, machines, pairs = pf_gold[f"{tag}_dims"]
+    t = po.tables(inst, heads_mode=1)
+    assert (t.jobs, t.machines, t.pairs) == (jobs, machines, pairs)
+    np.testing.assert_array_equal(t.arr("p_times", jobs * machines), pf_gold[f"{tag}_p_times"])
+    np.testing.assert_array_equal(t.arr("min_heads", machines), pf_gold[f"{tag}_min_heads_C"])
+    np.testing.assert_array_equal(t.arr("min_tails", machines), pf_gold[f"{tag}_min_tails"])
+    np.testing.assert_array_equal(t.arr("lags", pairs * jobs), pf_gold[f"{tag}_lags"])
+    np.testing.assert_array_equal(t.arr("mp0", pairs), pf_gold[f"{tag}_mp0"])
+    np.testing.assert_array_equal(t.arr("mp1", pairs), pf_gold[f"{tag}_mp1"])
+    # Johnson order: a permutation per pair, sorted by the same key as the reference's (ties may permute)
+    ours = t.arr("johnson", pairs * jobs).reshape(pairs, jobs)
+    ref = pf_gold[f"{tag}_johnson_qsort"].reshape(pairs, jobs)
+    p = pf_gold[f"{tag}_p_times"].reshape(machines, jobs)
+    lags = pf_gold[f"{tag}_lags"].reshape(pairs, jobs)
+    for k in range(pairs):
+        assert sorted(ours[k]) == list(range(jobs))
+        a = p[pf_gold[f"{tag}_mp0"][k]] + lags[k]
+        b = p[pf_gold[f"{tag}_mp1"][k]] + lags[k]
+        key = lambda j: (0, a[j]) if a[j] < b[j] else (1, -b[j])  # noqa: E731
+        assert [key(j) for j in ours[k]] == [key(j) for j in ref[k]]
+
+
+def test_chapel_min_heads_known_answers(counts):
+    for inst, name in ((14, "ta014"), (20, "ta020")):
+        t = po.tables(inst, heads_mode=0)
+        assert list(t.arr("min_heads", t.machines)) == counts["chapel_min_heads"][name]
+
+
+@pytest.mark.parametrize("inst", [1, 14, 20, 21])
+def test_bounds_match_reference(pf_gold, inst):
+    tag = f"ta{inst:03d}"
+    jobs = int(pf_gold[f"{tag}_dims"][0])
+    parents = pf_gold[f"{tag}_parents"].view(po.PFSP_NODE_DTYPE)
+    best = int(po.lib().or_taillard_best_ub(inst))
+    for heads_mode in (0, 1):  # min_heads is never read when limit1 >= 0
+        t = po.tables(inst, heads_mode)
+        np.testing.assert_array_equal(po.pfsp_evaluate(t, 1, parents, best), pf_gold[f"{tag}_lb1"])
+        np.testing.assert_array_equal(po.pfsp_evaluate(t, 0, parents, best), pf_gold[f"{tag}_lb1_d"])
+        np.testing.assert_array_equal(po.pfsp_evaluate(t, 2, parents, best), pf_gold[f"{tag}_lb2_best"])
+        np.testing.assert_array_equal(po.pfsp_evaluate(t, 2, parents, INT_MAX), pf_gold[f"{tag}_lb2_inf"])
+        np.testing.assert_array_equal(po.pfsp_evaluate(t, 2, parents, 2**63 - 1), pf_gold[f"{tag}_lb2_inf"])
+    # root (limit1 = -1), lb1_d, C min_heads semantics
+    root = np.zeros(1, dtype=po.PFSP_NODE_DTYPE)
+    root["limit1"][0] = -1
+    root["prmu"][0, :jobs] = np.arange(jobs)
+    np.testing.assert_array_equal(po.pfsp_evaluate(po.tables(inst, 1), 0, root, best), pf_gold[f"{tag}_root_lb1_d_C"])
+    # known answers: eval_solution / lb1 / lb2 on the identity permutation
+    ident = np.arange(jobs, dtype=np.int32)
+    t = po.tables(inst, 0)
+    import ctypes as C
+    p = ident.ctypes.data_as(C.c_void_p)
+    kat = [po.lib().or_eval_solution(C.byref(t), p), po.lib().or_lb1_bound(C.byref(t), p, 0, jobs),
+           po.lib().or_lb2_bound(C.byref(t), p, 0, jobs, INT_MAX)]
+    assert kat == list(pf_gold[f"{tag}_kat"])
+
+
+def test_survey_known_answers():
+    t = po.tables(14, 0)
+    assert list(t.arr("p_times", 20)) == [94, 43, 6, 47, 45, 51, 73, 49, 31, 58, 19, 36, 54, 75, 7, 5, 82, 20, 31, 32]
+    assert list(t.arr("min_tails", 10)) == [280, 205, 115, 110, 100, 78, 50, 31, 8, 0]
+    assert int(t.arr("p_times", 200).sum()) == 8930
+
+
+@pytest.mark.parametrize("N", list(range(4, 13)))
+def test_nq_search_counts(counts, N):
+    want = counts["nqueens"][str(N)]
+    assert want["sol"] == counts["nqueens_classical_solutions"][str(N)]
+    r = po.nq_search_seq(N)
+    assert (r.tree, r.sol) == (want["tree"], want["sol"])
+    for (m, M, D) in ((25, 50000, 1), (5, 300, 1), (25, 50000, 2), (7, 1000, 4)):
+        r = po.nq_search_offload(N, 1, m, M, D)
+        assert (r.tree, r.sol) == (want["tree"], want["sol"]), (m, M, D)
+
+
+@pytest.mark.parametrize("lb", [0, 1, 2])
+def test_pfsp_search_counts_ta014(counts, lb):
+    want = counts["pfsp"][f"ta014_lb{lb}_ub1"]
+    for heads_mode in (0, 1):  # ta014 counts do not depend on the min_heads quirk
+        if lb == 1 and heads_mode == 1:
+            continue
+        r = po.pfsp_search_seq(14, lb, 1, heads_mode)
+        assert (r.tree, r.sol, r.best) == (want["tree"], want["sol"], want["best"])
+    for (m, M, D) in ((25, 50000, 1), (25, 50000, 4)):
+        r = po.pfsp_search_offload(14, lb, 1, m, M, D)
+        assert (r.tree, r.sol, r.best) == (want["tree"], want["sol"], want["best"]), (m, M, D)
