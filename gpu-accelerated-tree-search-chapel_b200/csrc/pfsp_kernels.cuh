@@ -1,0 +1,301 @@
+// pfsp_kernels.cuh — PFSP lower bounds lb1 / lb1_d / lb2 over a chunk of parent nodes, sm_100a.
+//
+// Reference kernels replaced: evaluate_gpu_lb1 (pfsp_gpu_chpl.chpl:192-208), evaluate_gpu_lb1_d
+// (:216-235), evaluate_gpu_lb2 (:238-254) and the device math they call in
+// lib/pfsp/Bound_simple.chpl / Bound_johnson.chpl.  The reference runs one thread per child
+// slot (lb1, lb2), each of which re-copies the 88-byte parent and recomputes the parent's
+// front/remain from scratch.  Here the chunk streams through shared memory by TMA bulk copies
+// (tiles of 128 parents: 11 264 B in, 128*jobs*4 B out), the instance tables are staged into
+// shared memory once per CTA by one bulk copy, and the prefix work shared by all children of a
+// parent (front = completion times of the scheduled prefix, remain = unscheduled work per
+// machine) is computed ONCE per parent:
+//     child front   fc = add_forward(front, job)                (Bound_simple.chpl:29-35)
+//     child remain  rc[j] = remain[j] - p[j][job]               (sum_unscheduled :94-106 on the child)
+// which is exact integer arithmetic, so every bound is bit-identical to the reference.
+#pragma once
+#include "tsb_ptx.cuh"
+
+namespace tsb {
+
+constexpr int PF_THREADS = 128;
+constexpr int PF_TILE = 128;  // parents per tile (one per thread in the lb1 kernels)
+constexpr int PF_REC = 88;    // sizeof(tsb_pfsp_node)
+constexpr int PF_MAXJ = 20;
+constexpr int PF_MAXM = 20;
+constexpr int PF_MAXP = 190;
+
+// Instance tables as staged into shared memory (one 16-B-multiple blob per handle).
+struct PfspLb1Tables {
+  int32_t jobs, machines, pairs, mp;   // mp = machines rounded up to a multiple of 4
+  int32_t total[PF_MAXM];              // sum_j p[k][j]
+  int32_t min_heads[PF_MAXM];
+  int32_t min_tails[PF_MAXM];
+  int32_t pj[PF_MAXJ * PF_MAXM];       // job-major: pj[job*mp + k]
+};
+struct PfspLb2Tables {
+  int32_t pm[PF_MAXM * PF_MAXJ];       // machine-major as given: pm[k*jobs + job]
+  int32_t mp0[PF_MAXP + 2], mp1[PF_MAXP + 2], order[PF_MAXP + 2];
+  int32_t johnson[PF_MAXP * PF_MAXJ];  // [pair*jobs + pos] -> job
+  int32_t lags[PF_MAXP * PF_MAXJ];     // [pair*jobs + job]
+};
+static_assert(sizeof(PfspLb1Tables) % 16 == 0, "blob must be a multiple of 16 B");
+static_assert(sizeof(PfspLb2Tables) % 16 == 0, "blob must be a multiple of 16 B");
+
+__device__ __forceinline__ void stage_blob(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_g2s(dst_smem, src_gmem, bytes, bar);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+}
+
+// ------------------------------------------------------------------------------------------- lb1 / lb1_d
+constexpr int LB1_STAGES = 4;
+template <int JOBS_OUT>
+using Lb1Tiles = TileSmem<LB1_STAGES, PF_TILE * PF_REC, PF_TILE * JOBS_OUT * 4>;
+
+struct Lb1Smem {
+  Lb1Tiles<PF_MAXJ> tiles;
+  alignas(16) PfspLb1Tables tab;
+  alignas(8) uint64_t tab_bar;
+};
+
+// load row `job` of the job-major table: M machine times
+template <int M>
+__device__ __forceinline__ void load_row(const PfspLb1Tables& tab, int job, int (&row)[M]) {
+  constexpr int MP = (M + 3) & ~3;
+  const int4* src = reinterpret_cast<const int4*>(&tab.pj[job * MP]);
+#pragma unroll
+  for (int q = 0; q < MP / 4; q++) {
+    const int4 v = src[q];
+    if (4 * q + 0 < M) row[4 * q + 0] = v.x;
+    if (4 * q + 1 < M) row[4 * q + 1] = v.y;
+    if (4 * q + 2 < M) row[4 * q + 2] = v.z;
+    if (4 * q + 3 < M) row[4 * q + 3] = v.w;
+  }
+}
+
+// front/remain of the parent's scheduled prefix prmu[0..limit1]  (schedule_front :47-62 +
+// sum_unscheduled :94-106 rewritten as total - scheduled)
+template <int M>
+__device__ __forceinline__ void parent_front_remain(const PfspLb1Tables& tab, const int32_t* node, int limit1,
+                                                    bool heads_if_root, int (&F)[M], int (&R)[M]) {
+#pragma unroll
+  for (int j = 0; j < M; j++) {
+    F[j] = 0;
+    R[j] = tab.total[j];
+  }
+  if (limit1 < 0) {
+    if (heads_if_root) {
+#pragma unroll
+      for (int j = 0; j < M; j++) F[j] = tab.min_heads[j];
+    }
+    return;
+  }
+  for (int i = 0; i <= limit1; i++) {
+    int row[M];
+    load_row<M>(tab, node[2 + i], row);
+    F[0] += row[0];
+    R[0] -= row[0];
+#pragma unroll
+    for (int j = 1; j < M; j++) {
+      F[j] = max(F[j - 1], F[j]) + row[j];
+      R[j] -= row[j];
+    }
+  }
+}
+
+// KIND 1: lb1_bound on the child (Bound_simple.chpl:123-136, machine_bound_from_parts :108-121)
+// KIND 0: add_front_and_bound (Bound_simple.chpl:197-222)
+template <int KIND, int M>
+__device__ __forceinline__ int child_bound(const int (&F)[M], const int (&R)[M], const int (&B)[M],
+                                           const int (&row)[M]) {
+  if constexpr (KIND == 1) {
+    int fc = F[0] + row[0];              // child front, machine 0
+    int tmp0 = fc + (R[0] - row[0]);     // front_c[0] + remain_c[0]
+    int lb = tmp0 + B[0];
+#pragma unroll
+    for (int i = 1; i < M; i++) {
+      fc = max(fc, F[i]) + row[i];
+      const int tmp1 = max(tmp0, fc + (R[i] - row[i]));
+      lb = max(lb, tmp1 + B[i]);
+      tmp0 = tmp1;
+    }
+    return lb;
+  } else {
+    int lb = F[0] + R[0] + B[0];
+    int tmp0 = F[0] + row[0];
+#pragma unroll
+    for (int i = 1; i < M; i++) {
+      const int tmp1 = max(tmp0, F[i]);
+      lb = max(lb, tmp1 + R[i] + B[i]);
+      tmp0 = tmp1 + row[i];
+    }
+    return lb;
+  }
+}
+
+template <int KIND, int M>
+__device__ __forceinline__ void lb1_compute_tile(const PfspLb1Tables& tab, const uint8_t* in_tile,
+                                                 uint8_t* out_tile, int records) {
+  const int t = threadIdx.x;
+  const int jobs = tab.jobs;
+  const int32_t* node = reinterpret_cast<const int32_t*>(in_tile) + 22 * t;
+  int32_t* out = reinterpret_cast<int32_t*>(out_tile) + jobs * t;
+  if (t >= records) return;
+  const int limit1 = node[1];
+  int F[M], R[M], B[M];
+  parent_front_remain<M>(tab, node, limit1, KIND == 0, F, R);
+#pragma unroll
+  for (int j = 0; j < M; j++) B[j] = tab.min_tails[j];  // schedule_back with limit2 == jobs (:70-74)
+  for (int k = 0; k < jobs; k++) {
+    int v = 0;
+    if (k > limit1) {
+      int row[M];
+      load_row<M>(tab, node[2 + k], row);
+      v = child_bound<KIND, M>(F, R, B, row);
+    }
+    out[k] = v;
+  }
+}
+
+template <int KIND, int M>
+__global__ void __launch_bounds__(PF_THREADS) pfsp_lb1_kernel(const uint8_t* __restrict__ parents,
+                                                             uint8_t* __restrict__ bounds, long long count,
+                                                             const PfspLb1Tables* __restrict__ tables) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  Lb1Smem& sm = *reinterpret_cast<Lb1Smem*>(smem_raw);
+  stage_blob(&sm.tab, tables, sizeof(PfspLb1Tables), &sm.tab_bar);
+  const PfspLb1Tables& tab = sm.tab;
+  run_tile_pipeline<LB1_STAGES, PF_TILE, PF_REC, PF_MAXJ * 4>(
+      sm.tiles, parents, bounds, count, [&tab](const uint8_t* in_tile, uint8_t* out_tile, int n) {
+        lb1_compute_tile<KIND, M>(tab, in_tile, out_tile, n);
+      });
+}
+
+// ------------------------------------------------------------------------------------------- lb2
+// lb2_bound (Bound_johnson.chpl:274-289): front/back as above, flags of scheduled jobs
+// (set_flags :179-186, here a 20-bit register mask), then lb_makespan (:214-240) over the
+// machine pairs in machine_pair_order with compute_cmax_johnson (:188-212) per pair and the
+// early exit `lb > best` reproduced exactly (first pair, in order, where the running max
+// exceeds best).
+// Two phases per tile so that every lane carries a live child: (A) one thread per parent
+// computes the parent front and appends its live (parent, slot) items to a shared list;
+// (B) threads take items round-robin and run the pair loop for one child each.
+constexpr int LB2_STAGES = 2;
+using Lb2Tiles = TileSmem<LB2_STAGES, PF_TILE * PF_REC, PF_TILE * PF_MAXJ * 4>;
+
+struct Lb2Smem {
+  Lb2Tiles tiles;
+  alignas(16) PfspLb1Tables tab1;
+  alignas(16) PfspLb2Tables tab2;
+  alignas(8) uint64_t tab_bar[2];
+  int32_t front[PF_MAXM][PF_TILE];        // parent fronts, [machine][parent]
+  int32_t fc[PF_MAXM][PF_THREADS];        // per-thread child front scratch, [machine][thread]
+  uint32_t sched[PF_TILE];                // bit j set <=> job j scheduled in the parent
+  uint16_t items[PF_TILE * PF_MAXJ];      // (parent << 5) | slot
+  int32_t n_items;
+};
+
+template <int M>
+__device__ __forceinline__ void lb2_compute_tile(Lb2Smem& sm, const uint8_t* in_tile, uint8_t* out_tile,
+                                                 int records, int best) {
+  const int t = threadIdx.x;
+  const PfspLb1Tables& tab = sm.tab1;
+  const PfspLb2Tables& t2 = sm.tab2;
+  const int jobs = tab.jobs;
+  const int32_t* nodes = reinterpret_cast<const int32_t*>(in_tile);
+  int32_t* out = reinterpret_cast<int32_t*>(out_tile);
+
+  if (t == 0) sm.n_items = 0;
+  __syncthreads();
+  // ---- phase A
+  if (t < records) {
+    const int32_t* node = nodes + 22 * t;
+    const int limit1 = node[1];
+    int F[M], R[M];
+    parent_front_remain<M>(tab, node, limit1, false, F, R);  // lb2 children always have limit1 >= 0
+#pragma unroll
+    for (int j = 0; j < M; j++) sm.front[j][t] = F[j];
+    uint32_t mask = 0;
+    for (int i = 0; i <= limit1; i++) mask |= 1u << node[2 + i];
+    sm.sched[t] = mask;
+    const int live = jobs - 1 - limit1;
+    int base = live > 0 ? atomicAdd(&sm.n_items, live) : 0;
+    for (int k = 0; k < jobs; k++) {
+      if (k > limit1)
+        sm.items[base++] = static_cast<uint16_t>((t << 5) | k);
+      else
+        out[jobs * t + k] = 0;
+    }
+  }
+  __syncthreads();
+  // ---- phase B
+  const int n_items = sm.n_items;
+  const int pairs = tab.pairs;
+  for (int it = t; it < n_items; it += PF_THREADS) {
+    const int item = sm.items[it];
+    const int p = item >> 5, k = item & 31;
+    const int job = nodes[22 * p + 2 + k];
+    const uint32_t mask = sm.sched[p] | (1u << job);
+    {  // child front = add_forward(parent front, job)
+      int row[M];
+      load_row<M>(tab, job, row);
+      int f = sm.front[0][p] + row[0];
+      sm.fc[0][t] = f;
+#pragma unroll
+      for (int j = 1; j < M; j++) {
+        f = max(f, sm.front[j][p]) + row[j];
+        sm.fc[j][t] = f;
+      }
+    }
+    int lb = 0;
+    for (int l = 0; l < pairs; l++) {
+      const int i = t2.order[l];
+      const int ma0 = t2.mp0[i], ma1 = t2.mp1[i];
+      int tmp0 = sm.fc[ma0][t], tmp1 = sm.fc[ma1][t];
+      const int32_t* js = &t2.johnson[i * jobs];
+      const int32_t* lg = &t2.lags[i * jobs];
+      const int32_t* p0 = &t2.pm[ma0 * jobs];
+      const int32_t* p1 = &t2.pm[ma1 * jobs];
+      for (int j = 0; j < jobs; j++) {
+        const int jb = js[j];
+        if (!((mask >> jb) & 1u)) {
+          tmp0 += p0[jb];
+          tmp1 = max(tmp1, tmp0 + lg[jb]) + p1[jb];
+        }
+      }
+      tmp1 = max(tmp1 + tab.min_tails[ma1], tmp0 + tab.min_tails[ma0]);
+      lb = max(lb, tmp1);
+      if (lb > best) break;
+    }
+    out[jobs * p + k] = lb;
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(PF_THREADS) pfsp_lb2_kernel(const uint8_t* __restrict__ parents,
+                                                             uint8_t* __restrict__ bounds, long long count,
+                                                             const PfspLb1Tables* __restrict__ tables1,
+                                                             const PfspLb2Tables* __restrict__ tables2, int best) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  Lb2Smem& sm = *reinterpret_cast<Lb2Smem*>(smem_raw);
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.tab_bar[0], 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&sm.tab_bar[0], sizeof(PfspLb1Tables) + sizeof(PfspLb2Tables));
+    bulk_g2s(&sm.tab1, tables1, sizeof(PfspLb1Tables), &sm.tab_bar[0]);
+    bulk_g2s(&sm.tab2, tables2, sizeof(PfspLb2Tables), &sm.tab_bar[0]);
+  }
+  __syncthreads();
+  mbar_wait(&sm.tab_bar[0], 0);
+  run_tile_pipeline<LB2_STAGES, PF_TILE, PF_REC, PF_MAXJ * 4>(
+      sm.tiles, parents, bounds, count, [&sm, best](const uint8_t* in_tile, uint8_t* out_tile, int n) {
+        lb2_compute_tile<M>(sm, in_tile, out_tile, n, best);
+      });
+}
+
+}  // namespace tsb

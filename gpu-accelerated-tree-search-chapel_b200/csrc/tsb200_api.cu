@@ -1,0 +1,487 @@
+// tsb200_api.cu — C ABI of libtsb200.so (include/tsb200.h): handles, transfers, kernel launches.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "nq_kernel.cuh"
+#include "pfsp_kernels.cuh"
+#include "tsb200.h"
+
+namespace {
+
+thread_local std::string g_last_cuda_error;
+
+#define TSB_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      g_last_cuda_error = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+      (void)cudaGetLastError();                                                                \
+      return e__ == cudaErrorMemoryAllocation ? TSB_ENOMEM : TSB_ECUDA;                        \
+    }                                                                                          \
+  } while (0)
+
+int env_xfer() {
+  const char* s = std::getenv("TSB200_XFER");
+  if (!s) return TSB_XFER_AUTO;
+  if (!std::strcmp(s, "memcpy")) return TSB_XFER_MEMCPY;
+  if (!std::strcmp(s, "zerocopy")) return TSB_XFER_ZEROCOPY;
+  return TSB_XFER_AUTO;
+}
+bool env_no_register() {
+  const char* s = std::getenv("TSB200_NO_REGISTER");
+  return s && *s && *s != '0';
+}
+
+// Host ranges kept page-locked + mapped between calls, so that cudaMemcpyAsync is truly
+// asynchronous on the caller's own arrays and the zero-copy kernels can address them.
+struct HostRange {
+  uintptr_t base;
+  size_t len;
+};
+struct HostRegistry {
+  std::vector<HostRange> ranges;
+  bool disabled = env_no_register();
+  // returns true if [p, p+bytes) is (now) page-locked
+  bool ensure(const void* p, size_t bytes) {
+    if (disabled || !p || !bytes) return false;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p), b = a + bytes;
+    for (auto& r : ranges)
+      if (a >= r.base && b <= r.base + r.len) return true;
+    // merge with any overlapping registered range (the caller's array seen with a larger count)
+    uintptr_t na = a, nb = b;
+    for (size_t i = 0; i < ranges.size();) {
+      const uintptr_t ra = ranges[i].base, rb = ra + ranges[i].len;
+      if (ra < nb && na < rb) {
+        cudaHostUnregister(reinterpret_cast<void*>(ra));
+        na = std::min(na, ra);
+        nb = std::max(nb, rb);
+        ranges.erase(ranges.begin() + i);
+      } else {
+        ++i;
+      }
+    }
+    if (cudaHostRegister(reinterpret_cast<void*>(na), nb - na, cudaHostRegisterPortable | cudaHostRegisterMapped) !=
+        cudaSuccess) {
+      (void)cudaGetLastError();
+      return false;
+    }
+    ranges.push_back({na, nb - na});
+    return true;
+  }
+  void release() {
+    for (auto& r : ranges) cudaHostUnregister(reinterpret_cast<void*>(r.base));
+    ranges.clear();
+  }
+};
+
+struct DeviceInfo {
+  int sms = 0;
+  bool can_use_host_ptr = false;
+};
+int query_device(int device, DeviceInfo& di) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return TSB_ENODEV;
+  }
+  if (device < 0 || device >= n) return TSB_ENODEV;
+  TSB_CUDA(cudaSetDevice(device));
+  TSB_CUDA(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, device));
+  int v = 0;
+  TSB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrCanUseHostPointerForRegisteredMem, device));
+  di.can_use_host_ptr = v != 0;
+  return TSB_OK;
+}
+
+// common part of both handle types
+struct Base {
+  int device = 0, M_max = 0, xfer = TSB_XFER_AUTO;
+  DeviceInfo di;
+  cudaStream_t stream = nullptr;
+  uint8_t *d_in = nullptr, *d_out = nullptr;  // device chunk buffers (M_max records)
+  uint8_t *h_in = nullptr, *h_out = nullptr;  // pinned+mapped staging, used when the caller's arrays cannot be locked
+  size_t in_rec = 0, out_rec = 0;
+  HostRegistry reg;
+  uint64_t launches = 0;
+
+  int init(int dev, int M, size_t irec, size_t orec) {
+    device = dev;
+    M_max = M;
+    in_rec = irec;
+    out_rec = orec;
+    xfer = env_xfer();
+    int rc = query_device(dev, di);
+    if (rc != TSB_OK) return rc;
+    TSB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    TSB_CUDA(cudaMalloc(&d_in, in_rec * M + 256));
+    TSB_CUDA(cudaMalloc(&d_out, out_rec * M + 256));
+    return TSB_OK;
+  }
+  int ensure_staging() {
+    if (!h_in) TSB_CUDA(cudaHostAlloc(&h_in, in_rec * M_max + 256, cudaHostAllocPortable | cudaHostAllocMapped));
+    if (!h_out) TSB_CUDA(cudaHostAlloc(&h_out, out_rec * M_max + 256, cudaHostAllocPortable | cudaHostAllocMapped));
+    return TSB_OK;
+  }
+  void fini() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    reg.release();
+    if (d_in) cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+    if (h_in) cudaFreeHost(h_in);
+    if (h_out) cudaFreeHost(h_out);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  // Host-buffer evaluation shared by N-Queens and PFSP.  `launch(in_dev, out_dev, count, stream)`
+  // enqueues the evaluator kernel.
+  template <class Launch>
+  int evaluate_host(const void* in, int count, void* out, Launch&& launch) {
+    const size_t in_b = in_rec * count, out_b = out_rec * count;
+    const bool in_locked = reg.ensure(in, in_b), out_locked = reg.ensure(out, out_b);
+    int mode = xfer == TSB_XFER_AUTO ? TSB_XFER_MEMCPY : xfer;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (mode == TSB_XFER_ZEROCOPY && !(in_locked && out_locked && aligned && di.can_use_host_ptr))
+      mode = TSB_XFER_MEMCPY;
+
+    if (mode == TSB_XFER_ZEROCOPY) {
+      // the kernel's TMA engine pulls the chunk over PCIe and pushes the results back: one launch,
+      // reads and writes overlap on the full-duplex link
+      int rc = launch(static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), count, stream);
+      if (rc != TSB_OK) return rc;
+      TSB_CUDA(cudaStreamSynchronize(stream));
+      return TSB_OK;
+    }
+    const void* src = in;
+    void* dst = out;
+    if (!in_locked || !out_locked) {
+      int rc = ensure_staging();
+      if (rc != TSB_OK) return rc;
+    }
+    if (!in_locked) {
+      std::memcpy(h_in, in, in_b);
+      src = h_in;
+    }
+    if (!out_locked) dst = h_out;
+    TSB_CUDA(cudaMemcpyAsync(d_in, src, in_b, cudaMemcpyHostToDevice, stream));
+    int rc = launch(d_in, d_out, count, stream);
+    if (rc != TSB_OK) return rc;
+    TSB_CUDA(cudaMemcpyAsync(dst, d_out, out_b, cudaMemcpyDeviceToHost, stream));
+    TSB_CUDA(cudaStreamSynchronize(stream));
+    if (!out_locked) std::memcpy(out, h_out, out_b);
+    return TSB_OK;
+  }
+};
+
+// persistent grid: enough CTAs to fill the GPU, never more than there are full tiles
+template <class K>
+int grid_for(K kernel, int threads, size_t smem, long long count, int tile, int sms, int* grid) {
+  int per_sm = 0;
+  TSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const long long tiles = std::max<long long>(1, count / tile);
+  *grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(per_sm) * sms));
+  return TSB_OK;
+}
+
+}  // namespace
+
+// ============================================================================ N-Queens
+struct tsb_nq : Base {
+  int N = 0, g = 1;
+  bool attr_set = false;
+};
+
+namespace {
+
+template <int N>
+int launch_nq_n(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
+  auto kernel = tsb::nq_evaluate_kernel<N>;
+  const size_t smem = sizeof(tsb::NqSmem<N>) + 128;
+  if (!h->attr_set) {
+    TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    h->attr_set = true;
+  }
+  int grid = 1;
+  int rc = grid_for(kernel, tsb::NQ_THREADS, smem, count, tsb::NQ_TILE, h->di.sms, &grid);
+  if (rc != TSB_OK) return rc;
+  kernel<<<grid, tsb::NQ_THREADS, smem, s>>>(in, out, count);
+  TSB_CUDA(cudaGetLastError());
+  h->launches++;
+  return TSB_OK;
+}
+
+int launch_nq(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
+  switch (h->N) {
+#define TSB_NQ_CASE(n) \
+  case n:              \
+    return launch_nq_n<n>(h, in, out, count, s);
+    TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
+    TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
+    TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
+    TSB_NQ_CASE(20)
+#undef TSB_NQ_CASE
+  }
+  return TSB_EINVAL;
+}
+
+}  // namespace
+
+// ============================================================================ PFSP
+struct tsb_pfsp : Base {
+  int jobs = 0, machines = 0, pairs = 0, mt = 0;  // mt = template machine count (5, 10 or 20)
+  tsb::PfspLb1Tables* d_tab1 = nullptr;
+  tsb::PfspLb2Tables* d_tab2 = nullptr;
+  bool attr_set[3] = {false, false, false};
+};
+
+namespace {
+
+template <int KIND, int M>
+int launch_lb1_km(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
+  auto kernel = tsb::pfsp_lb1_kernel<KIND, M>;
+  const size_t smem = sizeof(tsb::Lb1Smem) + 128;
+  if (!h->attr_set[KIND]) {
+    TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    h->attr_set[KIND] = true;
+  }
+  int grid = 1;
+  int rc = grid_for(kernel, tsb::PF_THREADS, smem, count, tsb::PF_TILE, h->di.sms, &grid);
+  if (rc != TSB_OK) return rc;
+  kernel<<<grid, tsb::PF_THREADS, smem, s>>>(in, out, count, h->d_tab1);
+  TSB_CUDA(cudaGetLastError());
+  h->launches++;
+  return TSB_OK;
+}
+
+template <int M>
+int launch_lb2_m(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count, int best, cudaStream_t s) {
+  auto kernel = tsb::pfsp_lb2_kernel<M>;
+  const size_t smem = sizeof(tsb::Lb2Smem) + 128;
+  if (!h->attr_set[2]) {
+    TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    h->attr_set[2] = true;
+  }
+  int grid = 1;
+  int rc = grid_for(kernel, tsb::PF_THREADS, smem, count, tsb::PF_TILE, h->di.sms, &grid);
+  if (rc != TSB_OK) return rc;
+  kernel<<<grid, tsb::PF_THREADS, smem, s>>>(in, out, count, h->d_tab1, h->d_tab2, best);
+  TSB_CUDA(cudaGetLastError());
+  h->launches++;
+  return TSB_OK;
+}
+
+int launch_pfsp(tsb_pfsp* h, int lb_kind, const uint8_t* in, uint8_t* out, long long count, int64_t best64,
+                cudaStream_t s) {
+  // bounds are int32 and `lb > best` can never hold for best >= INT32_MAX (Chapel's max(int) under --ub 0)
+  const int best = best64 > INT_MAX ? INT_MAX : best64 < INT_MIN ? INT_MIN : static_cast<int>(best64);
+#define TSB_PF_DISPATCH(M)                                                          \
+  if (lb_kind == TSB_LB1) return launch_lb1_km<1, M>(h, in, out, count, s);         \
+  if (lb_kind == TSB_LB1_D) return launch_lb1_km<0, M>(h, in, out, count, s);       \
+  return launch_lb2_m<M>(h, in, out, count, best, s);
+  if (h->mt == 5) { TSB_PF_DISPATCH(5) }
+  if (h->mt == 10) { TSB_PF_DISPATCH(10) }
+  TSB_PF_DISPATCH(20)
+#undef TSB_PF_DISPATCH
+}
+
+}  // namespace
+
+// ============================================================================ exported C ABI
+extern "C" {
+
+const char* tsb_version(void) { return "tsb200 0.1 (sm_100a)"; }
+
+const char* tsb_strerror(int code) {
+  switch (code) {
+    case TSB_OK: return "ok";
+    case TSB_EINVAL: return "invalid argument";
+    case TSB_ECUDA: return "CUDA runtime error (see tsb_last_cuda_error)";
+    case TSB_ENOMEM: return "out of memory";
+    case TSB_ENODEV: return "no such CUDA device";
+    case TSB_EALIGN: return "device pointer not 16-byte aligned";
+    case TSB_EUNSUPPORTED: return "unsupported instance shape (jobs must be 20, machines 1..20)";
+  }
+  return "unknown error";
+}
+const char* tsb_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+int tsb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return TSB_ENODEV;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------- N-Queens
+int tsb_nq_create(tsb_nq** out, int device, int N, int g, int M_max) {
+  if (!out || N < 1 || N > TSB_MAX_QUEENS || g < 1 || M_max < 1) return TSB_EINVAL;
+  tsb_nq* h = new (std::nothrow) tsb_nq();
+  if (!h) return TSB_ENOMEM;
+  h->N = N;
+  h->g = g;
+  int rc = h->init(device, M_max, sizeof(tsb_nq_node), static_cast<size_t>(N));
+  if (rc != TSB_OK) {
+    h->fini();
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return TSB_OK;
+}
+
+void tsb_nq_destroy(tsb_nq* h) {
+  if (!h) return;
+  h->fini();
+  delete h;
+}
+
+int tsb_nq_evaluate(tsb_nq* h, const void* parents, int count, uint8_t* labels) {
+  if (!h || count < 0 || count > h->M_max) return TSB_EINVAL;
+  if (count == 0) return TSB_OK;
+  if (!parents || !labels) return TSB_EINVAL;
+  TSB_CUDA(cudaSetDevice(h->device));
+  return h->evaluate_host(parents, count, labels, [h](const uint8_t* in, uint8_t* out, int n, cudaStream_t s) {
+    return launch_nq(h, in, out, n, s);
+  });
+}
+
+int tsb_nq_evaluate_device(tsb_nq* h, const void* parents_d, int count, uint8_t* labels_d, void* stream) {
+  if (!h || count < 0) return TSB_EINVAL;
+  if (count == 0) return TSB_OK;
+  if (!parents_d || !labels_d) return TSB_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(parents_d) | reinterpret_cast<uintptr_t>(labels_d)) & 15) return TSB_EALIGN;
+  TSB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  return launch_nq(h, static_cast<const uint8_t*>(parents_d), labels_d, count, s);
+}
+
+int tsb_nq_set_xfer(tsb_nq* h, int mode) {
+  if (!h || mode < 0 || mode > 2) return TSB_EINVAL;
+  h->xfer = mode;
+  return TSB_OK;
+}
+uint64_t tsb_nq_kernel_launches(const tsb_nq* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------- PFSP
+int tsb_pfsp_create(tsb_pfsp** out, int device, int jobs, int machines, int M_max, const int32_t* p_times,
+                    const int32_t* min_heads, const int32_t* min_tails, int nb_pairs, const int32_t* johnson,
+                    const int32_t* lags, const int32_t* mp0, const int32_t* mp1, const int32_t* mp_order) {
+  if (!out || !p_times || !min_heads || !min_tails || M_max < 1 || nb_pairs < 0) return TSB_EINVAL;
+  if (nb_pairs > 0 && (!johnson || !lags || !mp0 || !mp1 || !mp_order)) return TSB_EINVAL;
+  if (jobs != TSB_MAX_JOBS || machines < 1 || machines > TSB_MAX_MACHINES || nb_pairs > TSB_MAX_PAIRS)
+    return TSB_EUNSUPPORTED;
+  tsb_pfsp* h = new (std::nothrow) tsb_pfsp();
+  if (!h) return TSB_ENOMEM;
+  h->jobs = jobs;
+  h->machines = machines;
+  h->pairs = nb_pairs;
+  h->mt = machines <= 5 ? 5 : machines <= 10 ? 10 : 20;
+  int rc = h->init(device, M_max, sizeof(tsb_pfsp_node), static_cast<size_t>(jobs) * 4);
+  // tables -> device blobs (zero padding up to the template machine count is value-neutral:
+  // the reference itself evaluates 20-wide zero-padded tuples, lib/pfsp/Bound_simple.chpl:125-135)
+  std::vector<tsb::PfspLb1Tables> t1v(1);
+  std::vector<tsb::PfspLb2Tables> t2v(1);
+  tsb::PfspLb1Tables& t1 = t1v[0];
+  tsb::PfspLb2Tables& t2 = t2v[0];
+  std::memset(&t1, 0, sizeof(t1));
+  std::memset(&t2, 0, sizeof(t2));
+  const int mp = (h->mt + 3) & ~3;
+  t1.jobs = jobs;
+  t1.machines = machines;
+  t1.pairs = nb_pairs;
+  t1.mp = mp;
+  for (int k = 0; k < machines; k++) {
+    t1.min_heads[k] = min_heads[k];
+    t1.min_tails[k] = min_tails[k];
+    for (int j = 0; j < jobs; j++) {
+      t1.total[k] += p_times[k * jobs + j];
+      t1.pj[j * mp + k] = p_times[k * jobs + j];
+      t2.pm[k * jobs + j] = p_times[k * jobs + j];
+    }
+  }
+  bool bad = false;
+  for (int i = 0; i < nb_pairs; i++) {
+    t2.mp0[i] = mp0[i];
+    t2.mp1[i] = mp1[i];
+    t2.order[i] = mp_order[i];
+    bad |= mp0[i] < 0 || mp0[i] >= machines || mp1[i] < 0 || mp1[i] >= machines || mp_order[i] < 0 ||
+           mp_order[i] >= nb_pairs;
+    for (int j = 0; j < jobs; j++) {
+      t2.johnson[i * jobs + j] = johnson[i * jobs + j];
+      t2.lags[i * jobs + j] = lags[i * jobs + j];
+      bad |= johnson[i * jobs + j] < 0 || johnson[i * jobs + j] >= jobs;
+    }
+  }
+  if (rc == TSB_OK && bad) rc = TSB_EINVAL;
+  auto upload = [&]() -> int {
+    TSB_CUDA(cudaMalloc(&h->d_tab1, sizeof(t1)));
+    TSB_CUDA(cudaMalloc(&h->d_tab2, sizeof(t2)));
+    TSB_CUDA(cudaMemcpy(h->d_tab1, &t1, sizeof(t1), cudaMemcpyHostToDevice));
+    TSB_CUDA(cudaMemcpy(h->d_tab2, &t2, sizeof(t2), cudaMemcpyHostToDevice));
+    return TSB_OK;
+  };
+  if (rc == TSB_OK) rc = upload();
+  if (rc != TSB_OK) {
+    tsb_pfsp_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return TSB_OK;
+}
+
+void tsb_pfsp_destroy(tsb_pfsp* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->d_tab1) cudaFree(h->d_tab1);
+  if (h->d_tab2) cudaFree(h->d_tab2);
+  h->fini();
+  delete h;
+}
+
+int tsb_pfsp_evaluate(tsb_pfsp* h, int lb_kind, const void* parents, int count, int64_t best, int32_t* bounds) {
+  if (!h || count < 0 || count > h->M_max || lb_kind < 0 || lb_kind > 2) return TSB_EINVAL;
+  if (lb_kind == TSB_LB2 && h->pairs == 0) return TSB_EINVAL;
+  if (count == 0) return TSB_OK;
+  if (!parents || !bounds) return TSB_EINVAL;
+  TSB_CUDA(cudaSetDevice(h->device));
+  return h->evaluate_host(parents, count, bounds,
+                          [h, lb_kind, best](const uint8_t* in, uint8_t* out, int n, cudaStream_t s) {
+                            return launch_pfsp(h, lb_kind, in, out, n, best, s);
+                          });
+}
+
+int tsb_pfsp_evaluate_device(tsb_pfsp* h, int lb_kind, const void* parents_d, int count, int64_t best,
+                             int32_t* bounds_d, void* stream) {
+  if (!h || count < 0 || lb_kind < 0 || lb_kind > 2) return TSB_EINVAL;
+  if (lb_kind == TSB_LB2 && h->pairs == 0) return TSB_EINVAL;
+  if (count == 0) return TSB_OK;
+  if (!parents_d || !bounds_d) return TSB_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(parents_d) | reinterpret_cast<uintptr_t>(bounds_d)) & 15) return TSB_EALIGN;
+  TSB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  return launch_pfsp(h, lb_kind, static_cast<const uint8_t*>(parents_d), reinterpret_cast<uint8_t*>(bounds_d),
+                     count, best, s);
+}
+
+int tsb_pfsp_set_xfer(tsb_pfsp* h, int mode) {
+  if (!h || mode < 0 || mode > 2) return TSB_EINVAL;
+  h->xfer = mode;
+  return TSB_OK;
+}
+uint64_t tsb_pfsp_kernel_launches(const tsb_pfsp* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

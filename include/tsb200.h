@@ -1,0 +1,170 @@
+/*
+ * tsb200.h — C ABI of libtsb200.so, the B200-native (sm_100a) batch node-evaluation engine.
+ *
+ * Drop-in boundary for the GPU offload step of the reference's Chapel drivers
+ * (Guillaume-Helbecque/GPU-accelerated-tree-search-Chapel).  Paths below are relative to the
+ * reference root.  Every entry point takes plain pointers and sizes, returns an int status
+ * (0 = TSB_OK, negative = TSB_E*), never throws, never calls exit(), and calls
+ * cudaSetDevice(handle->device) first (Chapel tasks share OS worker threads).
+ *
+ * One handle per (task, device); distinct handles are fully concurrent, a handle is not
+ * re-entrant.  The library owns all device and pinned staging memory; caller pointers are
+ * never retained past return, except that host ranges may stay page-locked (cudaHostRegister)
+ * between calls for speed (disable with env TSB200_NO_REGISTER=1) — tsb_*_destroy() releases them.
+ *
+ * Node wire formats (must match the Chapel records bit for bit):
+ *   N-Queens  lib/nqueens/NQueens_node.chpl:9-11   { uint8 depth; uint8 board[20]; }   21 B, align 1
+ *   PFSP      lib/pfsp/PFSP_node.chpl:9-12         { int32 depth; int32 limit1; int32 prmu[20]; } 88 B
+ *
+ * Output contract (same as the reference kernels): only slots k >= depth (N-Queens) /
+ * k >= limit1+1 (PFSP) are defined by the reference; this library additionally writes 0 to the
+ * slots below the live range (the reference leaves them stale; its consumer never reads them,
+ * nqueens_gpu_chpl.chpl:137-138, pfsp_gpu_chpl.chpl:280-281).
+ */
+#ifndef TSB200_H
+#define TSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSB_MAX_QUEENS 20
+#define TSB_MAX_JOBS 20
+#define TSB_MAX_MACHINES 20
+#define TSB_MAX_PAIRS 190
+
+typedef struct {
+  uint8_t depth;
+  uint8_t board[TSB_MAX_QUEENS];
+} tsb_nq_node; /* 21 bytes */
+
+typedef struct {
+  int32_t depth;
+  int32_t limit1;
+  int32_t prmu[TSB_MAX_JOBS];
+} tsb_pfsp_node; /* 88 bytes */
+
+enum {
+  TSB_OK = 0,
+  TSB_EINVAL = -1,   /* bad argument (NULL handle, N out of 1..20, count > M_max, unknown lb_kind ...) */
+  TSB_ECUDA = -2,    /* a CUDA runtime call failed; tsb_last_cuda_error() has the text */
+  TSB_ENOMEM = -3,   /* host or device allocation failed */
+  TSB_ENODEV = -4,   /* no such CUDA device / no CUDA driver */
+  TSB_EALIGN = -5,   /* device pointer passed to *_evaluate_device is not 16-byte aligned */
+  TSB_EUNSUPPORTED = -6 /* instance shape outside jobs <= 20, machines in 1..20 */
+};
+
+/* lower-bound selector: integer encoding of baselines/pfsp/pfsp_c.c:86-88 and
+ * baselines/pfsp/lib/evaluate.cu:93-115 (Chapel spells them "lb1_d" | "lb1" | "lb2",
+ * pfsp_gpu_chpl.chpl:15,257-270) */
+enum { TSB_LB1_D = 0, TSB_LB1 = 1, TSB_LB2 = 2 };
+
+/* host<->device transfer strategy of the host-buffer entry points */
+enum {
+  TSB_XFER_AUTO = 0,    /* pick per call (default; env TSB200_XFER=memcpy|zerocopy overrides) */
+  TSB_XFER_MEMCPY = 1,  /* cudaMemcpyAsync of the live prefix, kernel, cudaMemcpyAsync back */
+  TSB_XFER_ZEROCOPY = 2 /* the kernel's TMA engine reads/writes page-locked host memory over PCIe */
+};
+
+const char* tsb_strerror(int code);
+const char* tsb_last_cuda_error(void); /* thread-local text of the last failing CUDA call */
+int tsb_device_count(void);            /* >= 0, or TSB_ENODEV */
+const char* tsb_version(void);
+
+/* ------------------------------------------------------------------ N-Queens ------------- */
+typedef struct tsb_nq tsb_nq;
+
+/* Replaces the `on device var parents_d, labels_d` declarations, nqueens_gpu_chpl.chpl:194-195
+ * (multi-GPU: nqueens_multigpu_chpl.chpl:231-232).  N in 1..20, g >= 1 (results do not depend
+ * on g: the reference's inner `for _g` loop ANDs the same boolean g times, :115-118),
+ * M_max = the driver's --M (largest chunk). */
+int tsb_nq_create(tsb_nq** h, int device, int N, int g, int M_max);
+void tsb_nq_destroy(tsb_nq* h);
+
+/* Replaces the three statements of one offload round, nqueens_gpu_chpl.chpl:203-205
+ *   parents_d = parents;  on device do evaluate_gpu(parents_d, N*count, labels_d);  labels = labels_d;
+ * parents: count x 21 B host records; labels: count x N host bytes, labels[p*N + k] = 1 iff the
+ * queen board[k] can be placed on row `depth` (evaluate_gpu, nqueens_gpu_chpl.chpl:97-123).
+ * Synchronous; count == 0 is a no-op; only the live prefix moves (unlike Chapel's whole-array copy). */
+int tsb_nq_evaluate(tsb_nq* h, const void* parents, int count, uint8_t* labels);
+
+/* Device-resident form: evaluate_gpu itself (nqueens_gpu_chpl.chpl:97-123) on caller-owned device
+ * arrays (16-byte aligned), asynchronous on `stream` (a cudaStream_t; NULL = the handle's own
+ * stream).  count is not limited by M_max. */
+int tsb_nq_evaluate_device(tsb_nq* h, const void* parents_d, int count, uint8_t* labels_d, void* stream);
+
+int tsb_nq_set_xfer(tsb_nq* h, int mode);
+uint64_t tsb_nq_kernel_launches(const tsb_nq* h); /* kernels launched through this handle so far */
+
+/* ------------------------------------------------------------------ PFSP ----------------- */
+typedef struct tsb_pfsp tsb_pfsp;
+
+/* Replaces the device table set-up pfsp_gpu_chpl.chpl:359-371 (lbound1_d / lbound2_d); all
+ * tables are copied.  Layouts as in lb1_bound_data (lib/pfsp/Bound_simple.chpl:6-27) and
+ * lb2_bound_data (lib/pfsp/Bound_johnson.chpl:11-48):
+ *   p_times[machines*jobs] machine-major (k*jobs + job); min_heads/min_tails[machines];
+ *   johnson[nb_pairs*jobs], lags[nb_pairs*jobs]; mp0/mp1/mp_order[nb_pairs].
+ * jobs <= 20 (the reference's MAX_JOBS), machines <= 20, nb_pairs <= 190. */
+int tsb_pfsp_create(tsb_pfsp** h, int device, int jobs, int machines, int M_max, const int32_t* p_times,
+                    const int32_t* min_heads, const int32_t* min_tails, int nb_pairs,
+                    const int32_t* johnson, const int32_t* lags, const int32_t* mp0, const int32_t* mp1,
+                    const int32_t* mp_order);
+void tsb_pfsp_destroy(tsb_pfsp* h);
+
+/* Replaces pfsp_gpu_chpl.chpl:384-386
+ *   parents_d = parents; on device do evaluate_gpu(parents_d, jobs*count, best, lbound1_d, lbound2_d, bounds_d);
+ *   bounds = bounds_d;
+ * bounds[p*jobs + k] for k >= limit1+1 = lower bound of the child that schedules prmu[k] next:
+ * lb_kind TSB_LB1 -> evaluate_gpu_lb1 (:192-208), TSB_LB1_D -> evaluate_gpu_lb1_d (:216-235),
+ * TSB_LB2 -> evaluate_gpu_lb2 (:238-254) including its early exit against `best` (the value at
+ * launch for the whole chunk; Chapel int = int64, max(int) under --ub 0). */
+int tsb_pfsp_evaluate(tsb_pfsp* h, int lb_kind, const void* parents, int count, int64_t best, int32_t* bounds);
+int tsb_pfsp_evaluate_device(tsb_pfsp* h, int lb_kind, const void* parents_d, int count, int64_t best,
+                             int32_t* bounds_d, void* stream);
+int tsb_pfsp_set_xfer(tsb_pfsp* h, int mode);
+uint64_t tsb_pfsp_kernel_launches(const tsb_pfsp* h);
+
+/* ------------------------------------------------------------------ host-side problem data
+ * (CPU code the Chapel drivers already own — lib/pfsp/Taillard.chpl, fill_* in Bound_*.chpl —
+ * restated here only so that the C++ emulation drivers and the Python binding can run without
+ * Chapel; a Chapel build passes its own arrays to tsb_pfsp_create instead.) */
+typedef struct {
+  int32_t jobs, machines, pairs;
+  int32_t p_times[TSB_MAX_MACHINES * TSB_MAX_JOBS];
+  int32_t min_heads[TSB_MAX_MACHINES];
+  int32_t min_tails[TSB_MAX_MACHINES];
+  int32_t johnson[TSB_MAX_PAIRS * TSB_MAX_JOBS];
+  int32_t lags[TSB_MAX_PAIRS * TSB_MAX_JOBS];
+  int32_t mp0[TSB_MAX_PAIRS], mp1[TSB_MAX_PAIRS], mp_order[TSB_MAX_PAIRS];
+} tsb_pfsp_tables;
+
+int tsb_taillard_nb_jobs(int inst);      /* lib/pfsp/Taillard.chpl:29-36 */
+int tsb_taillard_nb_machines(int inst);  /* :38-52 */
+int64_t tsb_taillard_best_ub(int inst);  /* :54-70 */
+int tsb_pfsp_tables_build(tsb_pfsp_tables* t, int inst); /* pfsp_gpu_chpl.chpl:325-332, Chapel semantics */
+int tsb_pfsp_create_from_tables(tsb_pfsp** h, int device, int M_max, const tsb_pfsp_tables* t);
+
+/* ------------------------------------------------------------------ emulation of the Chapel drivers
+ * (same 3-step search, same Pool contract, same --m/--M/--D meaning; used for measurement
+ * because no Chapel compiler exists on the build/bench hosts).  D > 1 = static strided split
+ * of the warm-up pool over D GPUs, one host thread + handle + stream per GPU, no stealing. */
+typedef struct {
+  uint64_t explored_tree, explored_sol;
+  int64_t best;                   /* PFSP optimum (N-Queens: 0) */
+  double t_step1, t_step2, t_step3; /* seconds */
+  uint64_t offloads, offloaded_parents, kernel_launches;
+  uint64_t per_gpu_tree[8];
+} tsb_search_stats;
+
+/* nqueens_gpu_chpl.chpl:152-248 / nqueens_multigpu_chpl.chpl:158-352 */
+int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out);
+/* pfsp_gpu_chpl.chpl:306-431 / pfsp_multigpu_chpl.chpl:316-560 */
+int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSB200_H */

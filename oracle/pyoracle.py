@@ -209,6 +209,7 @@ def ref_nqueens() -> C.CDLL:
         # uint8_t isSafe(const int G, const uint8_t* board, const uint8_t queen_num, const uint8_t row_pos)
         L.isSafe.argtypes = [C.c_int, C.c_void_p, C.c_uint8, C.c_uint8]
         L.isSafe.restype = C.c_uint8
+        L.ref_nq_evaluate_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _ref_nq = L
     return _ref_nq
 
@@ -233,6 +234,8 @@ def ref_pfsp() -> C.CDLL:
         L.lb2_bound.restype = C.c_int
         L.eval_solution.argtypes = [C.POINTER(RefLb1), C.c_void_p]
         L.eval_solution.restype = C.c_int
+        L.ref_pfsp_evaluate_range.argtypes = [C.POINTER(RefLb1), C.POINTER(RefLb2), C.c_int, C.c_void_p, C.c_int,
+                                              C.c_int, C.c_int, C.c_void_p]
         _ref_pf = L
     return _ref_pf
 
