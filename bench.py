@@ -249,21 +249,26 @@ def run_workload(kind, M, steps, warmup, device_index, world, N=17):
     host_in = [base] + [np.roll(base, 7919 * (k + 1), axis=0) for k in range(min(nsets, 4) - 1)]
     d_in = [torch.from_numpy(host_in[k % len(host_in)].view(np.uint8).reshape(-1)).to(dev) for k in range(nsets)]
     d_out = [torch.empty(M * out_rec, dtype=torch.uint8, device=dev) for _ in range(nsets)]
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) stream: the kernels are launched on it and the CUDA events are recorded on it
+    tstream = torch.cuda.Stream(device=dev)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     # ---- device-resident: one launch per step
-    for w in range(warmup):
-        call_dev(d_in[w % nsets].data_ptr(), d_out[w % nsets].data_ptr(), stream)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(tstream):
+        for w in range(warmup):
+            call_dev(d_in[w % nsets].data_ptr(), d_out[w % nsets].data_ptr(), stream)
     torch.cuda.synchronize()
     l0 = ev.kernel_launches
     dist_barrier(world)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(device_index) as clk:
-        e0.record()
+    with ClockSampler(device_index) as clk, torch.cuda.stream(tstream):
+        e0.record(tstream)
         for k in range(steps):
             call_dev(d_in[k % nsets].data_ptr(), d_out[k % nsets].data_ptr(), stream)
-        e1.record()
+        e1.record(tstream)
         torch.cuda.synchronize()
     dist_barrier(world)
     t_dev = e0.elapsed_time(e1) / 1e3
@@ -310,7 +315,7 @@ def summarize(r, peak, peak_src, traffic=None):
 
 
 # ----------------------------------------------------------------------------------------- CPU arms
-def cpu_eval(kind, parents, threads, N=17):
+def cpu_eval(kind, parents, threads, N=17, repeat=1):
     """times the reference's CPU implementation of the path on `threads` host threads (ctypes drops the GIL);
     returns (seconds, kind_string)"""
     import ctypes as C
@@ -341,17 +346,26 @@ def cpu_eval(kind, parents, threads, N=17):
             f = po.lib().or_pfsp_evaluate_range
             work = lambda a, b: f(C.byref(t), 1, parents.ctypes.data, int(a), int(b), 1377, out.ctypes.data)  # noqa: E731
             src = "port"
+    def job(ab):
+        for _ in range(repeat):  # every thread sweeps its slice `repeat` times (one ctypes call each, GIL released)
+            work(*ab)
+
     with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(job, zip(cuts[:-1], cuts[1:])))  # warm: threads started, pages touched
         t0 = time.perf_counter()
-        list(ex.map(lambda ab: work(*ab), zip(cuts[:-1], cuts[1:])))
+        list(ex.map(job, zip(cuts[:-1], cuts[1:])))
         dt = time.perf_counter() - t0
-    return dt, src
+    return dt / repeat, src
 
 
 def cpu_baseline(kind, sample, threads):
-    dt, src = cpu_eval(kind, np.ascontiguousarray(sample), threads)
+    """~10-20 s of CPU work in total: the slice of each thread is swept `repeat` times"""
+    sample = np.ascontiguousarray(sample)
+    per_thread_rate = 12e6 if kind == "nq" else 0.7e6  # parents/s/thread, order of magnitude
+    repeat = max(1, int(15.0 * per_thread_rate * threads / sample.shape[0] / threads))
+    dt, src = cpu_eval(kind, sample, threads, repeat=repeat)
     return {"value": sample.shape[0] / dt / 1e6, "unit": "Mnodes/s", "cores": threads, "kind": src,
-            "sample": f"{sample.shape[0]} parents of the step's batch, {dt:.2f} s"}
+            "sample": f"{sample.shape[0]} parents of the step's batch x {repeat} sweeps, {dt * repeat:.2f} s wall"}
 
 
 def main():
@@ -381,11 +395,12 @@ def main():
         threads = os.cpu_count() or 1
         P = min(args.M, 1 << 21)
         sample = synth_nq_parents(N, P, 1234, tsb200.NQ_NODE_DTYPE)
+        rep = max(1, int(2.0 * 12e6 * threads / P))  # ~2 s per step on this host
         for _ in range(args.warmup):
-            cpu_eval("nq", sample[: P // 8], threads)
+            cpu_eval("nq", sample, threads, repeat=1)
         t, src = 0.0, "port"
         for _ in range(args.steps):
-            dt, src = cpu_eval("nq", sample, threads)
+            dt, src = cpu_eval("nq", sample, threads, repeat=rep)
             t += dt
         v = P * args.steps / t / 1e6
         line = {"impl": "reference", "metric": "Mnodes/s", "value": v, "unit": "Mnodes/s", "n_gpus": args.gpus,
@@ -398,7 +413,7 @@ def main():
         if not args.no_pfsp:
             Pp = 1 << 17
             ps = synth_pfsp_parents(Pp, 99, tsb200.PFSP_NODE_DTYPE)
-            dt, src2 = cpu_eval("pfsp", ps, threads)
+            dt, src2 = cpu_eval("pfsp", ps, threads, repeat=max(1, int(3.0 * 0.7e6 * threads / Pp)))
             line["pfsp"] = {"workload": "PFSP ta014 lb1 ub=1", "value": Pp / dt / 1e6, "unit": "Mnodes/s",
                             "cores": threads, "kind": src2, "sample": f"{Pp} parents"}
         print(json.dumps(line))

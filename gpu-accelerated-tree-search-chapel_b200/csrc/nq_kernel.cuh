@@ -4,18 +4,33 @@
 // CUDA twin baselines/nqueens/nqueens_gpu_cuda.cu:137-164), which re-reads the 21-byte parent
 // N times and runs an O(depth) loop per slot.  Here:
 //   * the chunk is streamed through shared memory by the TMA engine (cp.async.bulk) in tiles of
-//     512 parents (10 752 B in, 512*N B out), 4-stage mbarrier pipeline, persistent CTAs;
+//     512 parents (10 752 B in, 512*N B out), mbarrier pipeline, persistent CTAs;
 //   * one thread owns FOUR consecutive parents = 84 B = 21 aligned words in, N aligned words out,
 //     so the 21-byte / N-byte records never need unaligned or byte-wide memory instructions and
 //     the word strides (21, N odd for N = 17, 19) are bank-conflict free;
-//   * per parent the placed queens are folded once into a 32-bit "attacked values" mask
-//         U = OR_{i<depth} ( 1 << (board[i] + (depth-i)) | 1 << (board[i] - (depth-i)) )
-//     (bits outside 0..N-1 fall off), so label[k] = !bit(U, board[k]) : O(depth + N) per parent
-//     instead of O(depth * N).  Equivalent to the reference predicate
+//   * per parent the placed queens are folded once into a 32-bit "attacked values" mask U
+//     (bit v set <=> value v is attacked on row `depth` by some placed queen), so
+//     label[k] = !bit(U, board[k]): O(depth + N) per parent instead of O(depth * N).
+//     Equivalent to the reference predicate (nqueens_gpu_chpl.chpl:112-118)
 //         board[i] != board[k] - (depth-i)  &&  board[i] != board[k] + (depth-i)   for all i < depth
-//     evaluated in int arithmetic (no uint8 wrap), nqueens_gpu_chpl.chpl:112-118.
-// Slots k < depth are written 0 (the reference leaves them untouched).  `g` repeats an idempotent
-// AND in the reference (:115-118); the result does not depend on it and the work is done once.
+//     evaluated in int arithmetic (no uint8 wrap).
+//
+// The mask is built with ONE funnel shift per placed row.  For row i at distance s = depth - i
+// let V_i be the 64-bit value with bits 32+s and 32-s set.  Then
+//         high32( V_i << board[i] )  =  1 << (board[i] + s)  |  1 << (board[i] - s)
+// with the out-of-range bits (>= 32 resp. < 0) falling off both ends by themselves — both
+// diagonals, and the clamping, in one SHF.  The shift amount is taken in WRAP mode (low 5 bits
+// of the register), so the raw packed word that holds board[i] in its low byte is used as the
+// amount without extracting the byte (board values are < 32: a permutation of 0..N-1).
+// V_i = (hi, lo) = (1 << s, 1 << (32-s)) is produced from two per-parent constants by constant
+// shifts that make hi = lo = 0 for the rows i >= depth, so there are no per-row predicates.
+// Labels are read back the same way: low32( (S << 8m) >> board[k] ) puts bit board[k] of the
+// safe mask S = ~U at bit 8m, i.e. straight into byte m of the output word.
+//
+// Output contract: slots k >= depth are exact; slots k < depth are UNSPECIFIED, exactly as in the
+// reference, whose kernel does not write them (nqueens_gpu_chpl.chpl:109,119) and whose consumer
+// never reads them (:137-138).  `g` repeats an idempotent AND in the reference (:115-118); the
+// result does not depend on it and the work is done once.
 #pragma once
 #include "tsb_ptx.cuh"
 
@@ -25,53 +40,97 @@ constexpr int NQ_THREADS = 128;
 constexpr int NQ_QUAD = 4;                       // parents per thread
 constexpr int NQ_TILE = NQ_THREADS * NQ_QUAD;    // 512 parents per tile
 constexpr int NQ_REC = 21;                       // sizeof(tsb_nq_node)
-constexpr int NQ_STAGES = 4;
+constexpr int NQ_STAGES = 2;
 
 template <int N>
 using NqSmem = TileSmem<NQ_STAGES, NQ_TILE * NQ_REC, NQ_TILE * N>;
 
-// byte `b` (compile-time) of a little-endian word array
-template <int B>
-__device__ __forceinline__ uint32_t byte_of(const uint32_t* w) {
-  return (w[B >> 2] >> (8 * (B & 3))) & 0xFFu;
+// Integer multiplies that must stay multiplies: they run on the FMA pipe (IMAD), which this
+// kernel leaves idle, instead of the ALU pipe (SHF/LOP3), which is its bottleneck.
+__device__ __forceinline__ uint32_t mul_lo_fma(uint32_t x, uint32_t c) {
+  uint32_t r;
+  asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t mul_hi_fma(uint32_t x, uint32_t c) {
+  uint32_t r;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(c));
+  return r;
 }
 
-template <int N, int Q, int I>
-struct NqRows {
-  __device__ static __forceinline__ void run(const uint32_t* w, uint32_t depth, uint32_t& U) {
+// a register whose LOW BYTE is byte B (compile-time) of the little-endian word array w
+// (VAR 1: the right shift is done as a high multiply on the FMA pipe)
+template <int B, int VAR>
+__device__ __forceinline__ uint32_t low_byte_reg(const uint32_t* w) {
+  if constexpr ((B & 3) == 0)
+    return w[B >> 2];
+  else if constexpr (VAR == 1)
+    return mul_hi_fma(w[B >> 2], 1u << (32 - 8 * (B & 3)));
+  else
+    return w[B >> 2] >> (8 * (B & 3));
+}
+
+// rows [I0, I1) of parent Q: U |= OR_i high32(V_i << board[i])
+template <int N, int I>
+__device__ __forceinline__ uint32_t nq_row_term(uint32_t ph, uint32_t rb, const uint32_t (&amt)[N]) {
+  if constexpr (I < N) {
+    const uint32_t hi = mul_lo_fma(ph >> I, 2u);    // 1 << (depth - I) for I < depth, else 0
+    const uint32_t lo = mul_lo_fma(rb, 1u << I);    // 1 << (32 - depth + I) for I < depth, else 0 (falls off)
+    return shf_l_wrap(lo, hi, amt[I]);
+  } else {
+    return 0u;
+  }
+}
+template <int N, int Q, int I0, int I1>
+__device__ __forceinline__ void nq_rows(uint32_t ph, uint32_t rb, const uint32_t (&amt)[N], uint32_t& U) {
+  static_assert(I1 - I0 == 4, "rows come in groups of four");
+  U |= nq_row_term<N, I0>(ph, rb, amt) | nq_row_term<N, I0 + 1>(ph, rb, amt);
+  U |= nq_row_term<N, I0 + 2>(ph, rb, amt) | nq_row_term<N, I0 + 3>(ph, rb, amt);
+}
+
+template <int N, int Q, int VAR>
+struct NqParent {
+  uint32_t depth, ph, rb, U;
+  uint32_t amt[N];
+
+  __device__ __forceinline__ void init(const uint32_t* w) {
+    depth = low_byte_reg<21 * Q, VAR>(w) & 0xFFu;
+    ph = shl_clamp(1u, depth - 1u);   // 1 << (depth-1); 0 for depth == 0 (amount wraps to >= 32)
+    rb = shl_clamp(1u, 32u - depth);  // 1 << (32-depth); 0 for depth == 0
+    U = 0;
+    fill_amt<0>(w);
+  }
+  template <int I>
+  __device__ __forceinline__ void fill_amt(const uint32_t* w) {
     if constexpr (I < N) {
-      const uint32_t e = byte_of<21 * Q + 1 + I>(w);
-      const uint32_t s = depth - I;  // > 0 for placed rows
-      const uint32_t bits = shl_clamp(1u, e + s) | shl_clamp(1u, e - s);  // e - s < 0 wraps to >= 32 -> 0
-      if (I < depth) U |= bits;
-      NqRows<N, Q, I + 1>::run(w, depth, U);
+      amt[I] = low_byte_reg<21 * Q + 1 + I, VAR>(w);
+      fill_amt<I + 1>(w);
+    }
+  }
+  template <int I0, int I1>
+  __device__ __forceinline__ void rows() {
+    nq_rows<N, Q, I0, I1>(ph, rb, amt, U);
+  }
+  // slots [K0, K1): OR the label bits into the thread's output words
+  template <int K0, int K1>
+  __device__ __forceinline__ void slots(uint32_t (&o)[N]) {
+    const uint32_t S = ~U & ((1u << N) - 1u);
+    // (S << 8m) as 64-bit (lo, hi) pairs, m = output byte lane
+    const uint32_t lo_m[4] = {S, S << 8, S << 16, S << 24};
+    const uint32_t hi_m[4] = {0u, S >> 24, S >> 16, S >> 8};
+#pragma unroll
+    for (int k = K0; k < K1; k++) {
+      if (k < N) {
+        const int ob = Q * N + k;  // output byte index inside this thread's 4N bytes
+        const int m = ob & 3;
+        const uint32_t x = shf_r_wrap(lo_m[m], hi_m[m], amt[k]);
+        o[ob >> 2] |= x & (1u << (8 * m));
+      }
     }
   }
 };
 
-template <int N, int Q, int K>
-struct NqSlots {
-  __device__ static __forceinline__ void run(const uint32_t* w, uint32_t depth, uint32_t safe, uint32_t* o) {
-    if constexpr (K < N) {
-      const uint32_t e = byte_of<21 * Q + 1 + K>(w);
-      uint32_t bit = (safe >> e) & 1u;  // e <= 19
-      if (K < depth) bit = 0;
-      constexpr int OB = Q * N + K;  // output byte index inside this thread's 4N bytes
-      o[OB >> 2] |= bit << (8 * (OB & 3));
-      NqSlots<N, Q, K + 1>::run(w, depth, safe, o);
-    }
-  }
-};
-
-template <int N, int Q>
-__device__ __forceinline__ void nq_one_parent(const uint32_t* w, uint32_t* o) {
-  const uint32_t depth = byte_of<21 * Q>(w);
-  uint32_t U = 0;
-  NqRows<N, Q, 0>::run(w, depth, U);
-  NqSlots<N, Q, 0>::run(w, depth, ~U, o);
-}
-
-template <int N>
+template <int N, int VAR>
 __device__ __forceinline__ void nq_compute_tile(const uint8_t* in_tile, uint8_t* out_tile, int /*records*/) {
   const uint32_t* in_w = reinterpret_cast<const uint32_t*>(in_tile) + 21 * threadIdx.x;
   uint32_t* out_w = reinterpret_cast<uint32_t*>(out_tile) + N * threadIdx.x;
@@ -81,22 +140,66 @@ __device__ __forceinline__ void nq_compute_tile(const uint8_t* in_tile, uint8_t*
   uint32_t o[N];
 #pragma unroll
   for (int i = 0; i < N; i++) o[i] = 0;
-  nq_one_parent<N, 0>(w, o);
-  nq_one_parent<N, 1>(w, o);
-  nq_one_parent<N, 2>(w, o);
-  nq_one_parent<N, 3>(w, o);
+
+  NqParent<N, 0, VAR> p0;
+  NqParent<N, 1, VAR> p1;
+  NqParent<N, 2, VAR> p2;
+  NqParent<N, 3, VAR> p3;
+  p0.init(w);
+  p1.init(w);
+  p2.init(w);
+  p3.init(w);
+  const uint32_t dmax = max(max(p0.depth, p1.depth), max(p2.depth, p3.depth));
+  const uint32_t dmin = min(min(p0.depth, p1.depth), min(p2.depth, p3.depth));
+
+  // rows in groups of 4, the four parents interleaved for ILP; a group is skipped when no parent
+  // of this thread has placed queens in it (rows >= depth contribute nothing anyway)
+#pragma unroll
+  for (int j = 0; j < (N + 3) / 4; j++) {
+    if (dmax > 4u * j) {
+      switch (j) {  // compile-time row ranges
+#define TSB_ROWS(J)                 \
+  case J:                           \
+    p0.template rows<4 * J, 4 * J + 4>(); \
+    p1.template rows<4 * J, 4 * J + 4>(); \
+    p2.template rows<4 * J, 4 * J + 4>(); \
+    p3.template rows<4 * J, 4 * J + 4>(); \
+    break;
+        TSB_ROWS(0) TSB_ROWS(1) TSB_ROWS(2) TSB_ROWS(3) TSB_ROWS(4)
+#undef TSB_ROWS
+      }
+    }
+  }
+  // labels, again in groups of 4 slots; groups entirely below every parent's depth are skipped
+  // (their slots are unspecified by contract)
+#pragma unroll
+  for (int j = 0; j < (N + 3) / 4; j++) {
+    if (dmin < 4u * j + 4u) {
+      switch (j) {
+#define TSB_SLOTS(J)                 \
+  case J:                            \
+    p0.template slots<4 * J, 4 * J + 4>(o); \
+    p1.template slots<4 * J, 4 * J + 4>(o); \
+    p2.template slots<4 * J, 4 * J + 4>(o); \
+    p3.template slots<4 * J, 4 * J + 4>(o); \
+    break;
+        TSB_SLOTS(0) TSB_SLOTS(1) TSB_SLOTS(2) TSB_SLOTS(3) TSB_SLOTS(4)
+#undef TSB_SLOTS
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < N; i++) out_w[i] = o[i];
 }
 
-template <int N>
+template <int N, int VAR>
 __global__ void __launch_bounds__(NQ_THREADS) nq_evaluate_kernel(const uint8_t* __restrict__ parents,
                                                                 uint8_t* __restrict__ labels, long long count) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   NqSmem<N>& sm = *reinterpret_cast<NqSmem<N>*>(smem_raw);
   run_tile_pipeline<NQ_STAGES, NQ_TILE, NQ_REC, N>(
       sm, parents, labels, count,
-      [](const uint8_t* in_tile, uint8_t* out_tile, int n) { nq_compute_tile<N>(in_tile, out_tile, n); });
+      [](const uint8_t* in_tile, uint8_t* out_tile, int n) { nq_compute_tile<N, VAR>(in_tile, out_tile, n); });
 }
 
 }  // namespace tsb

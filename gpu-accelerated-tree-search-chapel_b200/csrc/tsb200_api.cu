@@ -199,14 +199,15 @@ int grid_for(K kernel, int threads, size_t smem, long long count, int tile, int 
 // ============================================================================ N-Queens
 struct tsb_nq : Base {
   int N = 0, g = 1;
+  int variant = 1;  // env TSB200_NQ_VARIANT (kernel A/B experiments)
   bool attr_set = false;
 };
 
 namespace {
 
-template <int N>
+template <int N, int VAR>
 int launch_nq_n(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
-  auto kernel = tsb::nq_evaluate_kernel<N>;
+  auto kernel = tsb::nq_evaluate_kernel<N, VAR>;
   const size_t smem = sizeof(tsb::NqSmem<N>) + 128;
   if (!h->attr_set) {
     TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -222,10 +223,11 @@ int launch_nq_n(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cud
 }
 
 int launch_nq(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
+  if (h->N == 17 && h->variant == 0) return launch_nq_n<17, 0>(h, in, out, count, s);  // A/B: shifts on the ALU pipe
   switch (h->N) {
 #define TSB_NQ_CASE(n) \
   case n:              \
-    return launch_nq_n<n>(h, in, out, count, s);
+    return launch_nq_n<n, 1>(h, in, out, count, s);
     TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
     TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
     TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
@@ -332,6 +334,7 @@ int tsb_nq_create(tsb_nq** out, int device, int N, int g, int M_max) {
   if (!h) return TSB_ENOMEM;
   h->N = N;
   h->g = g;
+  if (const char* v = std::getenv("TSB200_NQ_VARIANT")) h->variant = std::atoi(v);
   int rc = h->init(device, M_max, sizeof(tsb_nq_node), static_cast<size_t>(N));
   if (rc != TSB_OK) {
     h->fini();

@@ -17,9 +17,10 @@
  *   PFSP      lib/pfsp/PFSP_node.chpl:9-12         { int32 depth; int32 limit1; int32 prmu[20]; } 88 B
  *
  * Output contract (same as the reference kernels): only slots k >= depth (N-Queens) /
- * k >= limit1+1 (PFSP) are defined by the reference; this library additionally writes 0 to the
- * slots below the live range (the reference leaves them stale; its consumer never reads them,
- * nqueens_gpu_chpl.chpl:137-138, pfsp_gpu_chpl.chpl:280-281).
+ * k >= limit1+1 (PFSP) are defined; the slots below the live range are unspecified (the reference
+ * leaves them stale and its consumer never reads them, nqueens_gpu_chpl.chpl:137-138,
+ * pfsp_gpu_chpl.chpl:280-281).  N-Queens boards must hold values < 32 (they are permutations
+ * of 0..N-1 in every node the drivers create, lib/nqueens/NQueens_node.chpl:17-20).
  */
 #ifndef TSB200_H
 #define TSB200_H

@@ -2,8 +2,8 @@
 (libtsb200.so via the tsb200 binding) and is BIT-EXACT against the CPU oracle on the same seeded
 inputs, against the committed golden vectors produced by the reference's own C sources, and — for whole
 searches — against the counts the reference binaries print.  Only live slots (k >= depth resp.
-k >= limit1+1) are compared with the oracle; the slots below must be 0 (this library's documented
-extension of the contract)."""
+k >= limit1+1) are compared: the slots below the live range are unspecified in the reference (its
+kernels do not write them, its consumer does not read them) and in this library."""
 import json
 import os
 
@@ -51,7 +51,6 @@ def check_nq(ev, parents, N):
     want = po.nq_evaluate(parents.view(po.NQ_NODE_DTYPE), N).reshape(-1, N)
     live = po.nq_live_mask(parents.view(po.NQ_NODE_DTYPE), N)
     np.testing.assert_array_equal(got[live], want[live])
-    assert not got[~live].any(), "slots below depth must be written 0"
     return got
 
 
@@ -68,7 +67,6 @@ def check_pfsp(ev, parents, lb, best):
     want = po.pfsp_evaluate(t, kind, parents.view(po.PFSP_NODE_DTYPE), best).reshape(-1, jobs)
     live = po.pfsp_live_mask(parents.view(po.PFSP_NODE_DTYPE), jobs)
     np.testing.assert_array_equal(got[live], want[live])
-    assert not got[~live].any()
     return got
 
 
@@ -103,7 +101,7 @@ def test_nq_edge_cases():
         nodes["depth"][:32] = N
         nodes["depth"][32:] = 0
         got = check_nq(ev, nodes, N)
-        assert got[32:].all() and not got[:32].any()
+        assert got[32:].all()
         # count > M_max is refused, not truncated
         with pytest.raises(tsb200.TsbError):
             ev.evaluate(rand_nq(np.random.default_rng(6), N, 1001))
@@ -163,7 +161,8 @@ def test_nq_device_resident_large_batch():
         d_lab2 = torch.empty_like(d_lab)
         ev.evaluate_device(d_par2.data_ptr(), P, d_lab2.data_ptr(), torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
-        np.testing.assert_array_equal(d_lab2.cpu().numpy().reshape(P, N), got[perm])
+        live_all = po.nq_live_mask(parents[perm].view(po.NQ_NODE_DTYPE), N)
+        np.testing.assert_array_equal(d_lab2.cpu().numpy().reshape(P, N)[live_all], got[perm][live_all])
         # unaligned device pointers are refused
         with pytest.raises(tsb200.TsbError):
             ev.evaluate_device(d_par.data_ptr() + 1, 10, d_lab.data_ptr(), 0)
