@@ -111,13 +111,23 @@ struct NqParent {
   __device__ __forceinline__ void rows() {
     nq_rows<N, Q, I0, I1>(ph, rb, amt, U);
   }
+  // the safe-value mask S = ~U (N bits) pre-shifted to the four output byte lanes:
+  // (S << 8m) as 64-bit (lo_m, hi_m) pairs; S < 2^20, so hi_0 = hi_1 = 0
+  uint32_t lo_m[4], hi_m[4];
+  __device__ __forceinline__ void finish_mask() {
+    const uint32_t S = ~U & ((1u << N) - 1u);
+    lo_m[0] = S;
+    lo_m[1] = S << 8;
+    lo_m[2] = S << 16;
+    lo_m[3] = S << 24;
+    hi_m[0] = 0u;
+    hi_m[1] = 0u;
+    hi_m[2] = S >> 16;
+    hi_m[3] = S >> 8;
+  }
   // slots [K0, K1): OR the label bits into the thread's output words
   template <int K0, int K1>
   __device__ __forceinline__ void slots(uint32_t (&o)[N]) {
-    const uint32_t S = ~U & ((1u << N) - 1u);
-    // (S << 8m) as 64-bit (lo, hi) pairs, m = output byte lane
-    const uint32_t lo_m[4] = {S, S << 8, S << 16, S << 24};
-    const uint32_t hi_m[4] = {0u, S >> 24, S >> 16, S >> 8};
 #pragma unroll
     for (int k = K0; k < K1; k++) {
       if (k < N) {
@@ -170,6 +180,10 @@ __device__ __forceinline__ void nq_compute_tile(const uint8_t* in_tile, uint8_t*
       }
     }
   }
+  p0.finish_mask();
+  p1.finish_mask();
+  p2.finish_mask();
+  p3.finish_mask();
   // labels, again in groups of 4 slots; groups entirely below every parent's depth are skipped
   // (their slots are unspecified by contract)
 #pragma unroll

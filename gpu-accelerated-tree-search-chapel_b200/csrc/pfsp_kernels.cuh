@@ -26,11 +26,11 @@ constexpr int PF_MAXP = 190;
 
 // Instance tables as staged into shared memory (one 16-B-multiple blob per handle).
 struct PfspLb1Tables {
-  int32_t jobs, machines, pairs, mp;   // mp = machines rounded up to a multiple of 4
+  int32_t jobs, machines, pairs, mp;   // mp = row stride of pj in ints (row_stride())
   int32_t total[PF_MAXM];              // sum_j p[k][j]
   int32_t min_heads[PF_MAXM];
   int32_t min_tails[PF_MAXM];
-  int32_t pj[PF_MAXJ * PF_MAXM];       // job-major: pj[job*mp + k]
+  int32_t pj[PF_MAXJ * 22];            // job-major: pj[job*mp + k], mp = row_stride(template M)
 };
 struct PfspLb2Tables {
   int32_t pm[PF_MAXM * PF_MAXJ];       // machine-major as given: pm[k*jobs + job]
@@ -53,7 +53,13 @@ __device__ __forceinline__ void stage_blob(void* dst_smem, const void* src_gmem,
 }
 
 // ------------------------------------------------------------------------------------------- lb1 / lb1_d
-constexpr int LB1_STAGES = 4;
+// One thread per parent, 128 parents per tile.  Shared-memory traffic is the first bound of this
+// kernel (every parent touches all 20 job rows of the processing-time table exactly once: the
+// scheduled jobs in the front recurrence, the others as children), so every access is shaped to be
+// bank-conflict free: node words are read as 11 x LDS.64 (stride 88 B = odd multiple of 8 B), job
+// rows are `mp` ints at a stride of `mp` words read as LDS.64 (mp/2 odd for 10 machines), bounds
+// are written as 5 x STS.128 (stride 80 B = odd multiple of 16 B).
+constexpr int LB1_STAGES = 2;
 template <int JOBS_OUT>
 using Lb1Tiles = TileSmem<LB1_STAGES, PF_TILE * PF_REC, PF_TILE * JOBS_OUT * 4>;
 
@@ -63,23 +69,47 @@ struct Lb1Smem {
   alignas(8) uint64_t tab_bar;
 };
 
+// row stride (in ints) of the job-major table for a template machine count: even (LDS.64) and,
+// where possible, with an odd number of 8-byte units so that 16 lanes reading 16 different rows
+// hit 16 different bank pairs
+__host__ __device__ constexpr int row_stride(int M) { return M <= 5 ? 6 : M <= 10 ? 10 : 22; }
+
 // load row `job` of the job-major table: M machine times
 template <int M>
 __device__ __forceinline__ void load_row(const PfspLb1Tables& tab, int job, int (&row)[M]) {
-  constexpr int MP = (M + 3) & ~3;
-  const int4* src = reinterpret_cast<const int4*>(&tab.pj[job * MP]);
+  constexpr int MP = row_stride(M);
+  const int2* src = reinterpret_cast<const int2*>(&tab.pj[job * MP]);
 #pragma unroll
-  for (int q = 0; q < MP / 4; q++) {
-    const int4 v = src[q];
-    if (4 * q + 0 < M) row[4 * q + 0] = v.x;
-    if (4 * q + 1 < M) row[4 * q + 1] = v.y;
-    if (4 * q + 2 < M) row[4 * q + 2] = v.z;
-    if (4 * q + 3 < M) row[4 * q + 3] = v.w;
+  for (int q = 0; q < (M + 1) / 2; q++) {
+    const int2 v = src[q];
+    row[2 * q] = v.x;
+    if (2 * q + 1 < M) row[2 * q + 1] = v.y;
+  }
+}
+
+// integer add on the FMA pipe (IMAD): the max operations of the recurrences need the ALU pipe
+__device__ __forceinline__ int add_fma(int a, int b) {
+  int r;
+  asm("mad.lo.s32 %0, %1, 1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+// one scheduled job: front <- add_forward(front, job) (Bound_simple.chpl:29-35); remain -= p[.][job]
+template <int M>
+__device__ __forceinline__ void schedule_job(const PfspLb1Tables& tab, int job, int (&F)[M], int (&R)[M]) {
+  int row[M];
+  load_row<M>(tab, job, row);
+  F[0] = add_fma(F[0], row[0]);
+  R[0] = add_fma(R[0], -row[0]);
+#pragma unroll
+  for (int j = 1; j < M; j++) {
+    F[j] = add_fma(max(F[j - 1], F[j]), row[j]);
+    R[j] = add_fma(R[j], -row[j]);
   }
 }
 
 // front/remain of the parent's scheduled prefix prmu[0..limit1]  (schedule_front :47-62 +
-// sum_unscheduled :94-106 rewritten as total - scheduled)
+// sum_unscheduled :94-106 rewritten as total - scheduled).  Generic form reading prmu from memory.
 template <int M>
 __device__ __forceinline__ void parent_front_remain(const PfspLb1Tables& tab, const int32_t* node, int limit1,
                                                     bool heads_if_root, int (&F)[M], int (&R)[M]) {
@@ -95,17 +125,7 @@ __device__ __forceinline__ void parent_front_remain(const PfspLb1Tables& tab, co
     }
     return;
   }
-  for (int i = 0; i <= limit1; i++) {
-    int row[M];
-    load_row<M>(tab, node[2 + i], row);
-    F[0] += row[0];
-    R[0] -= row[0];
-#pragma unroll
-    for (int j = 1; j < M; j++) {
-      F[j] = max(F[j - 1], F[j]) + row[j];
-      R[j] -= row[j];
-    }
-  }
+  for (int i = 0; i <= limit1; i++) schedule_job<M>(tab, node[2 + i], F, R);
 }
 
 // KIND 1: lb1_bound on the child (Bound_simple.chpl:123-136, machine_bound_from_parts :108-121)
@@ -114,25 +134,26 @@ template <int KIND, int M>
 __device__ __forceinline__ int child_bound(const int (&F)[M], const int (&R)[M], const int (&B)[M],
                                            const int (&row)[M]) {
   if constexpr (KIND == 1) {
-    int fc = F[0] + row[0];              // child front, machine 0
-    int tmp0 = fc + (R[0] - row[0]);     // front_c[0] + remain_c[0]
+    int fc = add_fma(F[0], row[0]);              // child front, machine 0
+    int tmp0 = add_fma(fc, add_fma(R[0], -row[0]));  // front_c[0] + remain_c[0]
     int lb = tmp0 + B[0];
 #pragma unroll
     for (int i = 1; i < M; i++) {
-      fc = max(fc, F[i]) + row[i];
-      const int tmp1 = max(tmp0, fc + (R[i] - row[i]));
-      lb = max(lb, tmp1 + B[i]);
+      fc = add_fma(max(fc, F[i]), row[i]);
+      const int tmp1 = max(tmp0, add_fma(fc, add_fma(R[i], -row[i])));
+      lb = __viaddmax_s32(tmp1, B[i], lb);  // max(lb, tmp1 + back[i])
       tmp0 = tmp1;
     }
     return lb;
   } else {
-    int lb = F[0] + R[0] + B[0];
-    int tmp0 = F[0] + row[0];
+    // here R already holds remain[i] + back[i] (folded once per parent by the caller)
+    int lb = F[0] + R[0];
+    int tmp0 = add_fma(F[0], row[0]);
 #pragma unroll
     for (int i = 1; i < M; i++) {
       const int tmp1 = max(tmp0, F[i]);
-      lb = max(lb, tmp1 + R[i] + B[i]);
-      tmp0 = tmp1 + row[i];
+      lb = __viaddmax_s32(tmp1, R[i], lb);  // max(lb, tmp1 + remain[i] + back[i])
+      tmp0 = add_fma(tmp1, row[i]);
     }
     return lb;
   }
@@ -142,23 +163,52 @@ template <int KIND, int M>
 __device__ __forceinline__ void lb1_compute_tile(const PfspLb1Tables& tab, const uint8_t* in_tile,
                                                  uint8_t* out_tile, int records) {
   const int t = threadIdx.x;
-  const int jobs = tab.jobs;
-  const int32_t* node = reinterpret_cast<const int32_t*>(in_tile) + 22 * t;
-  int32_t* out = reinterpret_cast<int32_t*>(out_tile) + jobs * t;
   if (t >= records) return;
-  const int limit1 = node[1];
-  int F[M], R[M], B[M];
-  parent_front_remain<M>(tab, node, limit1, KIND == 0, F, R);
+  // the node: 22 ints as 11 conflict-free 8-byte loads
+  const int2* node2 = reinterpret_cast<const int2*>(in_tile) + 11 * t;
+  int prmu[PF_MAXJ];
+  const int2 head = node2[0];
+  const int limit1 = head.y;
 #pragma unroll
-  for (int j = 0; j < M; j++) B[j] = tab.min_tails[j];  // schedule_back with limit2 == jobs (:70-74)
-  for (int k = 0; k < jobs; k++) {
-    int v = 0;
-    if (k > limit1) {
-      int row[M];
-      load_row<M>(tab, node[2 + k], row);
-      v = child_bound<KIND, M>(F, R, B, row);
+  for (int q = 0; q < 10; q++) {
+    const int2 v = node2[1 + q];
+    prmu[2 * q] = v.x;
+    prmu[2 * q + 1] = v.y;
+  }
+  int F[M], R[M], B[M];
+#pragma unroll
+  for (int j = 0; j < M; j++) {
+    F[j] = 0;
+    R[j] = tab.total[j];
+    B[j] = tab.min_tails[j];  // schedule_back with limit2 == jobs (:70-74)
+  }
+  if (KIND == 0 && limit1 < 0) {  // lb1_d on the root: front = min_heads (schedule_front :53-57)
+#pragma unroll
+    for (int j = 0; j < M; j++) F[j] = tab.min_heads[j];
+  }
+#pragma unroll
+  for (int i = 0; i < PF_MAXJ; i++) {
+    if (i > limit1) break;
+    schedule_job<M>(tab, prmu[i], F, R);
+  }
+  if constexpr (KIND == 0) {  // fold remain + back once per parent
+#pragma unroll
+    for (int j = 0; j < M; j++) R[j] += B[j];
+  }
+  int4* out4 = reinterpret_cast<int4*>(out_tile) + 5 * t;
+#pragma unroll
+  for (int g = 0; g < 5; g++) {
+    int v[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int k = 4 * g + c;
+      if (k > limit1) {
+        int row[M];
+        load_row<M>(tab, prmu[k], row);
+        v[c] = child_bound<KIND, M>(F, R, B, row);
+      }
     }
-    out[k] = v;
+    out4[g] = make_int4(v[0], v[1], v[2], v[3]);
   }
 }
 

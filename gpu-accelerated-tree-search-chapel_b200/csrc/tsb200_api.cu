@@ -401,7 +401,7 @@ int tsb_pfsp_create(tsb_pfsp** out, int device, int jobs, int machines, int M_ma
   tsb::PfspLb2Tables& t2 = t2v[0];
   std::memset(&t1, 0, sizeof(t1));
   std::memset(&t2, 0, sizeof(t2));
-  const int mp = (h->mt + 3) & ~3;
+  const int mp = tsb::row_stride(h->mt);
   t1.jobs = jobs;
   t1.machines = machines;
   t1.pairs = nb_pairs;
