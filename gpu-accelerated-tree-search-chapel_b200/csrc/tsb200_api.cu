@@ -107,7 +107,9 @@ int query_device(int device, DeviceInfo& di) {
 struct Base {
   int device = 0, M_max = 0, xfer = TSB_XFER_AUTO;
   DeviceInfo di;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  int pipe_min = 131072;  // records from which the memcpy path is split over two streams (env TSB200_PIPE_MIN)
+  int pipe_chunk = 262144;
   uint8_t *d_in = nullptr, *d_out = nullptr;  // device chunk buffers (M_max records)
   uint8_t *h_in = nullptr, *h_out = nullptr;  // pinned+mapped staging, used when the caller's arrays cannot be locked
   size_t in_rec = 0, out_rec = 0;
@@ -123,6 +125,9 @@ struct Base {
     int rc = query_device(dev, di);
     if (rc != TSB_OK) return rc;
     TSB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    TSB_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    if (const char* v = std::getenv("TSB200_PIPE_MIN")) pipe_min = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("TSB200_PIPE_CHUNK")) pipe_chunk = std::max(1024, std::atoi(v)) & ~1023;
     TSB_CUDA(cudaMalloc(&d_in, in_rec * M + 256));
     TSB_CUDA(cudaMalloc(&d_out, out_rec * M + 256));
     return TSB_OK;
@@ -141,6 +146,7 @@ struct Base {
     if (h_in) cudaFreeHost(h_in);
     if (h_out) cudaFreeHost(h_out);
     if (stream) cudaStreamDestroy(stream);
+    if (stream2) cudaStreamDestroy(stream2);
   }
 
   // Host-buffer evaluation shared by N-Queens and PFSP.  `launch(in_dev, out_dev, count, stream)`
@@ -149,10 +155,12 @@ struct Base {
   int evaluate_host(const void* in, int count, void* out, Launch&& launch) {
     const size_t in_b = in_rec * count, out_b = out_rec * count;
     const bool in_locked = reg.ensure(in, in_b), out_locked = reg.ensure(out, out_b);
-    int mode = xfer == TSB_XFER_AUTO ? TSB_XFER_MEMCPY : xfer;
+    // AUTO: zero-copy whenever the caller's arrays could be page-locked and are 16-byte aligned (measured
+    // fastest at every chunk size, profiles/xfer_sweep_r1.txt); otherwise copies, pipelined when large
     const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-    if (mode == TSB_XFER_ZEROCOPY && !(in_locked && out_locked && aligned && di.can_use_host_ptr))
-      mode = TSB_XFER_MEMCPY;
+    const bool zc_ok = in_locked && out_locked && aligned && di.can_use_host_ptr;
+    int mode = xfer == TSB_XFER_AUTO ? (zc_ok ? TSB_XFER_ZEROCOPY : TSB_XFER_MEMCPY) : xfer;
+    if (mode == TSB_XFER_ZEROCOPY && !zc_ok) mode = TSB_XFER_MEMCPY;
 
     if (mode == TSB_XFER_ZEROCOPY) {
       // the kernel's TMA engine pulls the chunk over PCIe and pushes the results back: one launch,
@@ -173,11 +181,30 @@ struct Base {
       src = h_in;
     }
     if (!out_locked) dst = h_out;
-    TSB_CUDA(cudaMemcpyAsync(d_in, src, in_b, cudaMemcpyHostToDevice, stream));
-    int rc = launch(d_in, d_out, count, stream);
-    if (rc != TSB_OK) return rc;
-    TSB_CUDA(cudaMemcpyAsync(dst, d_out, out_b, cudaMemcpyDeviceToHost, stream));
-    TSB_CUDA(cudaStreamSynchronize(stream));
+    if (count >= pipe_min && count > pipe_chunk) {
+      // large chunk: sub-chunks alternate between two streams so that the upload of one overlaps the
+      // download of the previous one (PCIe is full duplex) and the kernel of the one in between
+      const cudaStream_t st[2] = {stream, stream2};
+      int i = 0;
+      for (int off = 0; off < count; off += pipe_chunk, ++i) {
+        const int n = std::min(pipe_chunk, count - off);
+        cudaStream_t s = st[i & 1];
+        TSB_CUDA(cudaMemcpyAsync(d_in + in_rec * off, static_cast<const uint8_t*>(src) + in_rec * off, in_rec * n,
+                                 cudaMemcpyHostToDevice, s));
+        int rc = launch(d_in + in_rec * off, d_out + out_rec * off, n, s);
+        if (rc != TSB_OK) return rc;
+        TSB_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + out_rec * off, d_out + out_rec * off, out_rec * n,
+                                 cudaMemcpyDeviceToHost, s));
+      }
+      TSB_CUDA(cudaStreamSynchronize(stream));
+      TSB_CUDA(cudaStreamSynchronize(stream2));
+    } else {
+      TSB_CUDA(cudaMemcpyAsync(d_in, src, in_b, cudaMemcpyHostToDevice, stream));
+      int rc = launch(d_in, d_out, count, stream);
+      if (rc != TSB_OK) return rc;
+      TSB_CUDA(cudaMemcpyAsync(dst, d_out, out_b, cudaMemcpyDeviceToHost, stream));
+      TSB_CUDA(cudaStreamSynchronize(stream));
+    }
     if (!out_locked) std::memcpy(out, h_out, out_b);
     return TSB_OK;
   }
@@ -185,10 +212,13 @@ struct Base {
 
 // persistent grid: enough CTAs to fill the GPU, never more than there are full tiles
 template <class K>
-int grid_for(K kernel, int threads, size_t smem, long long count, int tile, int sms, int* grid) {
-  int per_sm = 0;
-  TSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-  if (per_sm < 1) per_sm = 1;
+int grid_for(K kernel, int threads, size_t smem, long long count, int tile, int sms, int* grid, int* cache) {
+  int per_sm = *cache;
+  if (per_sm <= 0) {
+    TSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    *cache = per_sm;
+  }
   const long long tiles = std::max<long long>(1, count / tile);
   *grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(per_sm) * sms));
   return TSB_OK;
@@ -199,7 +229,8 @@ int grid_for(K kernel, int threads, size_t smem, long long count, int tile, int 
 // ============================================================================ N-Queens
 struct tsb_nq : Base {
   int N = 0, g = 1;
-  int variant = 1;  // env TSB200_NQ_VARIANT (kernel A/B experiments)
+  int variant = 0;  // env TSB200_NQ_VARIANT (kernel A/B experiments)
+  int occ = 0;      // cached CTAs per SM
   bool attr_set = false;
 };
 
@@ -214,7 +245,7 @@ int launch_nq_n(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cud
     h->attr_set = true;
   }
   int grid = 1;
-  int rc = grid_for(kernel, tsb::NQ_THREADS, smem, count, tsb::NQ_TILE, h->di.sms, &grid);
+  int rc = grid_for(kernel, tsb::NQ_THREADS, smem, count, tsb::NQ_TILE, h->di.sms, &grid, &h->occ);
   if (rc != TSB_OK) return rc;
   kernel<<<grid, tsb::NQ_THREADS, smem, s>>>(in, out, count);
   TSB_CUDA(cudaGetLastError());
@@ -223,11 +254,11 @@ int launch_nq_n(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cud
 }
 
 int launch_nq(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
-  if (h->N == 17 && h->variant == 0) return launch_nq_n<17, 0>(h, in, out, count, s);  // A/B: shifts on the ALU pipe
+  if (h->N == 17 && h->variant == 1) return launch_nq_n<17, 1>(h, in, out, count, s);  // A/B experiment: byte alignment as IMAD.HI
   switch (h->N) {
 #define TSB_NQ_CASE(n) \
   case n:              \
-    return launch_nq_n<n, 1>(h, in, out, count, s);
+    return launch_nq_n<n, 0>(h, in, out, count, s);
     TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
     TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
     TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
@@ -245,6 +276,7 @@ struct tsb_pfsp : Base {
   tsb::PfspLb1Tables* d_tab1 = nullptr;
   tsb::PfspLb2Tables* d_tab2 = nullptr;
   bool attr_set[3] = {false, false, false};
+  int occ[3] = {0, 0, 0};
 };
 
 namespace {
@@ -258,7 +290,7 @@ int launch_lb1_km(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count,
     h->attr_set[KIND] = true;
   }
   int grid = 1;
-  int rc = grid_for(kernel, tsb::PF_THREADS, smem, count, tsb::PF_TILE, h->di.sms, &grid);
+  int rc = grid_for(kernel, tsb::PF_THREADS, smem, count, tsb::PF_TILE, h->di.sms, &grid, &h->occ[KIND]);
   if (rc != TSB_OK) return rc;
   kernel<<<grid, tsb::PF_THREADS, smem, s>>>(in, out, count, h->d_tab1);
   TSB_CUDA(cudaGetLastError());
@@ -275,7 +307,7 @@ int launch_lb2_m(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count, 
     h->attr_set[2] = true;
   }
   int grid = 1;
-  int rc = grid_for(kernel, tsb::PF_THREADS, smem, count, tsb::PF_TILE, h->di.sms, &grid);
+  int rc = grid_for(kernel, tsb::PF_THREADS, smem, count, tsb::PF_TILE, h->di.sms, &grid, &h->occ[2]);
   if (rc != TSB_OK) return rc;
   kernel<<<grid, tsb::PF_THREADS, smem, s>>>(in, out, count, h->d_tab1, h->d_tab2, best);
   TSB_CUDA(cudaGetLastError());
