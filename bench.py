@@ -50,6 +50,11 @@ PFSP_TA014_LB1_HIST = {1: 1, 2: 39, 3: 165, 4: 639, 5: 2252, 6: 7003, 7: 19626, 
                        18: 21829, 19: 2648}
 
 
+# depth histogram of offloaded parents, ta020 lb2
+PFSP_TA020_LB2_HIST = {1: 8, 2: 92, 3: 597, 4: 3538, 5: 17546, 6: 71163, 7: 224227, 8: 533085, 9: 947932, 10: 1193333,
+                       11: 1044659, 12: 572606, 13: 205065, 14: 47233, 15: 7546, 16: 1526, 17: 208, 18: 13}
+
+
 # ----------------------------------------------------------------------------------------- synthetic inputs
 def nq_depth_hist(N):
     with open(_HIST_PATH) as f:
@@ -237,11 +242,13 @@ def run_workload(kind, M, steps, warmup, device_index, world, N=17):
         call_host = lambda par, out: ev.evaluate_gpu(par, M * N, out)  # noqa: E731
     else:
         in_rec, out_rec = 88, 80
-        make = lambda seed: synth_pfsp_parents(M, seed, tsb200.PFSP_NODE_DTYPE)  # noqa: E731
-        ev = tsb200.PfspEvaluator(14, M=M, device=device_index)
-        call_dev = lambda i, o, s: ev.evaluate_device("lb1", i, M, 1377, o, s)  # noqa: E731
+        inst, lb, best, hist = (14, "lb1", 1377, PFSP_TA014_LB1_HIST) if kind == "pfsp" else \
+            (20, "lb2", 1591, PFSP_TA020_LB2_HIST)
+        make = lambda seed: synth_pfsp_parents(M, seed, tsb200.PFSP_NODE_DTYPE, hist)  # noqa: E731
+        ev = tsb200.PfspEvaluator(inst, M=M, device=device_index)
+        call_dev = lambda i, o, s: ev.evaluate_device(lb, i, M, best, o, s)  # noqa: E731
         out_dtype, out_elems = np.int32, M * 20
-        call_host = lambda par, out: ev.evaluate_gpu(par, M * 20, 1377, "lb1", out)  # noqa: E731
+        call_host = lambda par, out: ev.evaluate_gpu(par, M * 20, best, lb, out)  # noqa: E731
     bytes_per_set = M * (in_rec + out_rec)
     nsets = max(2, int(np.ceil(2.5 * L2_BYTES / bytes_per_set)))  # rotate over > 2.5x L2 of distinct buffers
     nsets = min(nsets, 64)
@@ -378,6 +385,7 @@ def main():
     ap.add_argument("--pfsp-M", type=int, default=1 << 20)
     ap.add_argument("--no-pfsp", action="store_true")
     ap.add_argument("--no-small", action="store_true", help="skip the --M 50000 measurements")
+    ap.add_argument("--lb2", action="store_true", help="also time PFSP ta020 lb2 (BASELINE configs[3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, local_rank, world = dist_env()
@@ -451,6 +459,13 @@ def main():
             pf2 = run_workload("pfsp", 50000, max(args.steps * 5, 100), args.warmup, device_index, world)
             s2 = summarize(pf2, peak, peak_src)
             line["pfsp"]["at_M50000"] = {"value": s2["value"], "e2e": s2["e2e"], "roofline": s2["roofline"]}
+    if args.lb2:
+        l2 = run_workload("lb2", 1 << 18, max(3, args.steps // 10), args.warmup, device_index, world)
+        ls = summarize(l2, peak, peak_src)
+        line["pfsp_lb2"] = {"workload": "PFSP ta020 lb2 ub=1 (best=1591 at launch), synthetic parents with the "
+                            "ta020/lb2 offload depth histogram; int-ALU bound (O(pairs*jobs) per child)",
+                            "M": 1 << 18, "value": ls["value"], "unit": "Mnodes/s", "ms_per_step": ls["ms_per_step"],
+                            "e2e": ls["e2e"], "roofline": ls["roofline"], "gpu_launches": l2["launches"]}
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
         line["cpu_baseline"] = cpu_baseline("nq", big["sample"][: 1 << 21], threads)

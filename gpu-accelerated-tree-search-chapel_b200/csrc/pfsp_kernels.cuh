@@ -67,7 +67,32 @@ struct Lb1Smem {
   Lb1Tiles<PF_MAXJ> tiles;
   alignas(16) PfspLb1Tables tab;
   alignas(8) uint64_t tab_bar;
+  int32_t bin[32];            // per-tile histogram of parent depths, then exclusive prefix
+  uint8_t order[PF_TILE];     // parents of the tile sorted by depth
 };
+
+// Sort the parents of a tile by depth (counting sort in shared memory) and return the parent this
+// thread should process.  The per-parent work grows with depth in the front recurrence and shrinks
+// with it in the children loop, so a warp whose 32 parents have (nearly) the same depth executes
+// close to the average number of steps instead of max-prefix + max-children of a mixed warp.
+__device__ __forceinline__ int depth_sorted_parent(int32_t* bin, uint8_t* order, const uint8_t* in_tile,
+                                                   int records) {
+  const int t = threadIdx.x;
+  if (t < 32) bin[t] = 0;
+  __syncthreads();
+  int d = 31;  // threads beyond the tile's records sort last and stay idle
+  if (t < records) {
+    d = reinterpret_cast<const int32_t*>(in_tile)[22 * t + 1] + 1;  // limit1 + 1 in 0..20
+    d = min(max(d, 0), 30);
+  }
+  const int rank = atomicAdd(&bin[d], 1);
+  __syncthreads();
+  int base = 0;
+  for (int b = 0; b < d; b++) base += bin[b];  // broadcast reads
+  order[base + rank] = static_cast<uint8_t>(t);
+  __syncthreads();
+  return order[t];
+}
 
 // row stride (in ints) of the job-major table for a template machine count: even (LDS.64) and,
 // where possible, with an odd number of 8-byte units so that 16 lanes reading 16 different rows
@@ -160,11 +185,12 @@ __device__ __forceinline__ int child_bound(const int (&F)[M], const int (&R)[M],
 }
 
 template <int KIND, int M>
-__device__ __forceinline__ void lb1_compute_tile(const PfspLb1Tables& tab, const uint8_t* in_tile,
-                                                 uint8_t* out_tile, int records) {
-  const int t = threadIdx.x;
+__device__ __forceinline__ void lb1_compute_tile(Lb1Smem& sm, const uint8_t* in_tile, uint8_t* out_tile,
+                                                 int records) {
+  const PfspLb1Tables& tab = sm.tab;
+  const int t = depth_sorted_parent(sm.bin, sm.order, in_tile, records);
   if (t >= records) return;
-  // the node: 22 ints as 11 conflict-free 8-byte loads
+  // the node: 22 ints as 11 8-byte loads
   const int2* node2 = reinterpret_cast<const int2*>(in_tile) + 11 * t;
   int prmu[PF_MAXJ];
   const int2 head = node2[0];
@@ -219,10 +245,9 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_lb1_kernel(const uint8_t* __r
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Lb1Smem& sm = *reinterpret_cast<Lb1Smem*>(smem_raw);
   stage_blob(&sm.tab, tables, sizeof(PfspLb1Tables), &sm.tab_bar);
-  const PfspLb1Tables& tab = sm.tab;
   run_tile_pipeline<LB1_STAGES, PF_TILE, PF_REC, PF_MAXJ * 4>(
-      sm.tiles, parents, bounds, count, [&tab](const uint8_t* in_tile, uint8_t* out_tile, int n) {
-        lb1_compute_tile<KIND, M>(tab, in_tile, out_tile, n);
+      sm.tiles, parents, bounds, count, [&sm](const uint8_t* in_tile, uint8_t* out_tile, int n) {
+        lb1_compute_tile<KIND, M>(sm, in_tile, out_tile, n);
       });
 }
 
