@@ -59,7 +59,7 @@ __device__ __forceinline__ void stage_blob(void* dst_smem, const void* src_gmem,
 // bank-conflict free: node words are read as 11 x LDS.64 (stride 88 B = odd multiple of 8 B), job
 // rows are `mp` ints at a stride of `mp` words read as LDS.64 (mp/2 odd for 10 machines), bounds
 // are written as 5 x STS.128 (stride 80 B = odd multiple of 16 B).
-constexpr int LB1_STAGES = 2;
+constexpr int LB1_STAGES = 1;  // 21.5 KB of tiles per CTA -> 7 CTAs (28 warps) per SM; the CTAs overlap each other's loads
 template <int JOBS_OUT>
 using Lb1Tiles = TileSmem<LB1_STAGES, PF_TILE * PF_REC, PF_TILE * JOBS_OUT * 4>;
 
@@ -94,22 +94,18 @@ __device__ __forceinline__ int depth_sorted_parent(int32_t* bin, uint8_t* order,
   return order[t];
 }
 
-// row stride (in ints) of the job-major table for a template machine count: even (LDS.64) and,
-// where possible, with an odd number of 8-byte units so that 16 lanes reading 16 different rows
-// hit 16 different bank pairs
-__host__ __device__ constexpr int row_stride(int M) { return M <= 5 ? 6 : M <= 10 ? 10 : 22; }
+// row stride (in ints) of the job-major table for a template machine count: ODD, so that the 20 job
+// rows start in 20 different banks and a warp-wide 4-byte load of "machine k of each lane's job" is
+// always one conflict-free wavefront (lanes with the same job broadcast).  8-byte row loads were
+// measured at 1.6x the ideal wavefront count (16 bank pairs cannot hold 20 rows).
+__host__ __device__ constexpr int row_stride(int M) { return M | 1; }
 
 // load row `job` of the job-major table: M machine times
 template <int M>
 __device__ __forceinline__ void load_row(const PfspLb1Tables& tab, int job, int (&row)[M]) {
-  constexpr int MP = row_stride(M);
-  const int2* src = reinterpret_cast<const int2*>(&tab.pj[job * MP]);
+  const int32_t* src = &tab.pj[job * row_stride(M)];
 #pragma unroll
-  for (int q = 0; q < (M + 1) / 2; q++) {
-    const int2 v = src[q];
-    row[2 * q] = v.x;
-    if (2 * q + 1 < M) row[2 * q + 1] = v.y;
-  }
+  for (int q = 0; q < M; q++) row[q] = src[q];
 }
 
 // integer add on the FMA pipe (IMAD): the max operations of the recurrences need the ALU pipe
@@ -159,13 +155,16 @@ template <int KIND, int M>
 __device__ __forceinline__ int child_bound(const int (&F)[M], const int (&R)[M], const int (&B)[M],
                                            const int (&row)[M]) {
   if constexpr (KIND == 1) {
-    int fc = add_fma(F[0], row[0]);              // child front, machine 0
-    int tmp0 = add_fma(fc, add_fma(R[0], -row[0]));  // front_c[0] + remain_c[0]
+    // front_c[i] + remain_c[i] = (max(fc[i-1], F[i]) + p) + (R[i] - p) = max(fc[i-1], F[i]) + R[i]:
+    // the child's own processing time cancels exactly (integers)
+    int fc = add_fma(F[0], row[0]);  // child front, machine 0
+    int tmp0 = F[0] + R[0];          // front_c[0] + remain_c[0]
     int lb = tmp0 + B[0];
 #pragma unroll
     for (int i = 1; i < M; i++) {
-      fc = add_fma(max(fc, F[i]), row[i]);
-      const int tmp1 = max(tmp0, add_fma(fc, add_fma(R[i], -row[i])));
+      const int m = max(fc, F[i]);
+      fc = add_fma(m, row[i]);
+      const int tmp1 = max(tmp0, add_fma(m, R[i]));
       lb = __viaddmax_s32(tmp1, B[i], lb);  // max(lb, tmp1 + back[i])
       tmp0 = tmp1;
     }
@@ -212,29 +211,50 @@ __device__ __forceinline__ void lb1_compute_tile(Lb1Smem& sm, const uint8_t* in_
 #pragma unroll
     for (int j = 0; j < M; j++) F[j] = tab.min_heads[j];
   }
+  // two scheduled jobs per step: the second job's chain can start one machine behind the first
+  // one's (wavefront parallelism) when both sit in one branch-free block
 #pragma unroll
-  for (int i = 0; i < PF_MAXJ; i++) {
+  for (int i = 0; i < PF_MAXJ; i += 2) {
     if (i > limit1) break;
-    schedule_job<M>(tab, prmu[i], F, R);
+    if (i + 1 <= limit1) {
+      int r0[M], r1[M];
+      load_row<M>(tab, prmu[i], r0);
+      load_row<M>(tab, prmu[i + 1], r1);
+      int f0 = add_fma(F[0], r0[0]);
+      int f1 = add_fma(f0, r1[0]);
+      R[0] = add_fma(R[0], -add_fma(r0[0], r1[0]));
+      F[0] = f1;
+#pragma unroll
+      for (int j = 1; j < M; j++) {
+        f0 = add_fma(max(f0, F[j]), r0[j]);  // job i on machine j
+        f1 = add_fma(max(f1, f0), r1[j]);    // job i+1 on machine j
+        R[j] = add_fma(R[j], -add_fma(r0[j], r1[j]));
+        F[j] = f1;
+      }
+    } else {
+      schedule_job<M>(tab, prmu[i], F, R);
+    }
   }
   if constexpr (KIND == 0) {  // fold remain + back once per parent
 #pragma unroll
     for (int j = 0; j < M; j++) R[j] += B[j];
   }
   int4* out4 = reinterpret_cast<int4*>(out_tile) + 5 * t;
+  // children in groups of four slots = one 16-byte store.  A group with at least one live slot
+  // evaluates all four slots without branches (four independent recurrences to interleave); the
+  // values of slots k <= limit1 are unspecified by contract.
 #pragma unroll
   for (int g = 0; g < 5; g++) {
-    int v[4] = {0, 0, 0, 0};
+    if (4 * g + 3 > limit1) {
+      int v[4];
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const int k = 4 * g + c;
-      if (k > limit1) {
+      for (int c = 0; c < 4; c++) {
         int row[M];
-        load_row<M>(tab, prmu[k], row);
+        load_row<M>(tab, prmu[4 * g + c], row);
         v[c] = child_bound<KIND, M>(F, R, B, row);
       }
+      out4[g] = make_int4(v[0], v[1], v[2], v[3]);
     }
-    out4[g] = make_int4(v[0], v[1], v[2], v[3]);
   }
 }
 

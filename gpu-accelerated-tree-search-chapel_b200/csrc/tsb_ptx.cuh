@@ -152,11 +152,16 @@ __device__ __forceinline__ void run_tile_pipeline(Smem& sm, const uint8_t* __res
     fence_async_smem();
     // the store issued from out[(s+1)%STAGES] STAGES-1 iterations ago must have drained its
     // shared-memory reads before anyone writes that buffer in the next iteration
-    if (tid == 0) bulk_wait_read<STAGES - 2>();
+    if constexpr (STAGES >= 2) {
+      if (tid == 0) bulk_wait_read<(STAGES >= 2 ? STAGES - 2 : 0)>();
+    }
     __syncthreads();
     if (tid == 0) {
       bulk_s2g(out_g + tile * OUT_BYTES, sm.out[s], OUT_BYTES);
       bulk_commit();
+      // single-buffered: nobody can start the next tile before its load is issued below, so
+      // draining the store's shared-memory reads here protects the one output buffer
+      if constexpr (STAGES == 1) bulk_wait_read<0>();
       const long long nxt = it + STAGES;
       if (nxt < my_tiles) {
         mbar_arrive_expect_tx(&sm.full[s], IN_BYTES);
