@@ -190,11 +190,16 @@ def dist_env():
 
 def dist_init(backend):
     import torch.distributed as dist
-    _, _, world = dist_env()
+    _, local_rank, world = dist_env()
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
-        dist.init_process_group(backend=backend)
+        if backend == "nccl":
+            import torch
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend=backend, device_id=torch.device(f"cuda:{local_rank}"))
+        else:
+            dist.init_process_group(backend=backend)
     return world
 
 
@@ -334,28 +339,29 @@ def cpu_eval(kind, parents, threads, N=17, repeat=1):
     if kind == "nq":
         out = np.zeros(P * N, dtype=np.uint8)
         if po.ref_available():
-            f = po.ref_nqueens().ref_nq_evaluate_range
-            work = lambda a, b: f(parents.ctypes.data, int(a), int(b), N, 1, out.ctypes.data)  # noqa: E731
+            f = po.ref_nqueens().ref_nq_evaluate_range_rep
+            work = lambda a, b: f(parents.ctypes.data, int(a), int(b), N, 1, out.ctypes.data, repeat)  # noqa: E731
             src = "reference"
         else:
             f = po.lib().or_nq_evaluate_range
-            work = lambda a, b: f(parents.ctypes.data, int(a), int(b), N, 1, out.ctypes.data)  # noqa: E731
+            work = lambda a, b: [f(parents.ctypes.data, int(a), int(b), N, 1, out.ctypes.data)  # noqa: E731
+                                 for _ in range(repeat)]
             src = "port"
     else:
         out = np.zeros(P * 20, dtype=np.int32)
         if po.ref_available():
             d1, d2 = po.ref_pfsp_data(14)
-            f = po.ref_pfsp().ref_pfsp_evaluate_range
-            work = lambda a, b: f(d1, d2, 1, parents.ctypes.data, int(a), int(b), 1377, out.ctypes.data)  # noqa: E731
+            f = po.ref_pfsp().ref_pfsp_evaluate_range_rep
+            work = lambda a, b: f(d1, d2, 1, parents.ctypes.data, int(a), int(b), 1377, out.ctypes.data, repeat)  # noqa: E731
             src = "reference"
         else:
             t = po.tables(14)
             f = po.lib().or_pfsp_evaluate_range
-            work = lambda a, b: f(C.byref(t), 1, parents.ctypes.data, int(a), int(b), 1377, out.ctypes.data)  # noqa: E731
+            work = lambda a, b: [f(C.byref(t), 1, parents.ctypes.data, int(a), int(b), 1377, out.ctypes.data)  # noqa: E731
+                                 for _ in range(repeat)]
             src = "port"
-    def job(ab):
-        for _ in range(repeat):  # every thread sweeps its slice `repeat` times (one ctypes call each, GIL released)
-            work(*ab)
+    def job(ab):  # every thread sweeps its slice `repeat` times inside ONE foreign call (GIL released)
+        work(*ab)
 
     with ThreadPoolExecutor(max_workers=threads) as ex:
         list(ex.map(job, zip(cuts[:-1], cuts[1:])))  # warm: threads started, pages touched
@@ -375,11 +381,24 @@ def cpu_baseline(kind, sample, threads):
             "sample": f"{sample.shape[0]} parents of the step's batch x {repeat} sweeps, {dt * repeat:.2f} s wall"}
 
 
+def emit(line):
+    """print THE one JSON line on the real stdout (fd 1 is pointed at stderr while the bench runs, so that
+    libraries that write to stdout on their own — NCCL prints its version there — cannot pollute it)"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--M", type=int, default=1 << 22, help="parents per step and per GPU (the drivers' --M)")
     ap.add_argument("--pfsp-M", type=int, default=1 << 20)
@@ -424,7 +443,7 @@ def main():
             dt, src2 = cpu_eval("pfsp", ps, threads, repeat=max(1, int(3.0 * 0.7e6 * threads / Pp)))
             line["pfsp"] = {"workload": "PFSP ta014 lb1 ub=1", "value": Pp / dt / 1e6, "unit": "Mnodes/s",
                             "cores": threads, "kind": src2, "sample": f"{Pp} parents"}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -474,7 +493,7 @@ def main():
         if not args.no_pfsp:
             line["pfsp"]["cpu_baseline"] = cpu_baseline("pfsp", pf["sample"][: 1 << 17], threads)
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

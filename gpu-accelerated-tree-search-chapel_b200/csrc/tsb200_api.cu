@@ -359,6 +359,19 @@ int tsb_device_count(void) {
   return n;
 }
 
+int tsb_init_devices(int n) {
+  int have = 0;
+  if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1) {
+    (void)cudaGetLastError();
+    return TSB_ENODEV;
+  }
+  for (int d = 0; d < n && d < have; d++) {
+    TSB_CUDA(cudaSetDevice(d));
+    TSB_CUDA(cudaFree(nullptr));
+  }
+  return TSB_OK;
+}
+
 // ---------------------------------------------------------------- N-Queens
 int tsb_nq_create(tsb_nq** out, int device, int N, int g, int M_max) {
   if (!out || N < 1 || N > TSB_MAX_QUEENS || g < 1 || M_max < 1) return TSB_EINVAL;

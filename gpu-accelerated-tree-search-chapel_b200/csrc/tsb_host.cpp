@@ -414,6 +414,7 @@ int tsb_pfsp_create_from_tables(tsb_pfsp** h, int device, int M_max, const tsb_p
 int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out) {
   if (!out || N < 1 || N > TSB_MAX_QUEENS || g < 1 || m < 1 || M < 1 || D < 1 || D > 8) return TSB_EINVAL;
   std::memset(out, 0, sizeof(*out));
+  if (int rc = tsb_init_devices(D); rc != TSB_OK) return rc;  // contexts exist before the timers start
   Pool<tsb_nq_node> pool;
   tsb_nq_node root{};
   for (int i = 0; i < N; i++) root.board[i] = static_cast<uint8_t>(i);
@@ -469,6 +470,7 @@ int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_sear
   tsb_pfsp_tables& t = tv[0];
   int rc = tsb_pfsp_tables_build(&t, inst);
   if (rc != TSB_OK) return rc;
+  if (rc = tsb_init_devices(D); rc != TSB_OK) return rc;  // contexts exist before the timers start
   HostBounds hb(t);
   int64_t best = ub == 1 ? tsb_taillard_best_ub(inst) : INT64_MAX;  // pfsp_gpu_chpl.chpl:37
   Pool<tsb_pfsp_node> pool;

@@ -73,6 +73,9 @@ enum {
 const char* tsb_strerror(int code);
 const char* tsb_last_cuda_error(void); /* thread-local text of the last failing CUDA call */
 int tsb_device_count(void);            /* >= 0, or TSB_ENODEV */
+/* create the CUDA context of devices 0..n-1 now (the Chapel runtime does this at program start); the
+ * emulation drivers call it before starting their timers */
+int tsb_init_devices(int n);
 const char* tsb_version(void);
 
 /* ------------------------------------------------------------------ N-Queens ------------- */

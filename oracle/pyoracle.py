@@ -210,6 +210,7 @@ def ref_nqueens() -> C.CDLL:
         L.isSafe.argtypes = [C.c_int, C.c_void_p, C.c_uint8, C.c_uint8]
         L.isSafe.restype = C.c_uint8
         L.ref_nq_evaluate_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_nq_evaluate_range_rep.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         _ref_nq = L
     return _ref_nq
 
@@ -236,6 +237,8 @@ def ref_pfsp() -> C.CDLL:
         L.eval_solution.restype = C.c_int
         L.ref_pfsp_evaluate_range.argtypes = [C.POINTER(RefLb1), C.POINTER(RefLb2), C.c_int, C.c_void_p, C.c_int,
                                               C.c_int, C.c_int, C.c_void_p]
+        L.ref_pfsp_evaluate_range_rep.argtypes = [C.POINTER(RefLb1), C.POINTER(RefLb2), C.c_int, C.c_void_p, C.c_int,
+                                                  C.c_int, C.c_int, C.c_void_p, C.c_int]
         _ref_pf = L
     return _ref_pf
 

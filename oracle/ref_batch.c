@@ -23,6 +23,10 @@ void ref_nq_evaluate_range(const Node* parents, int begin, int end, int N, int G
       labels[(size_t)p * N + j] = isSafe(G, parents[p].board, depth, parents[p].board[j]);
   }
 }
+/* `repeat` sweeps in one call, so that a timing thread pays the call overhead once */
+void ref_nq_evaluate_range_rep(const Node* parents, int begin, int end, int N, int G, uint8_t* labels, int repeat) {
+  for (int r = 0; r < repeat; r++) ref_nq_evaluate_range(parents, begin, end, N, G, labels);
+}
 #endif
 
 #ifdef REF_BATCH_PFSP
@@ -51,5 +55,9 @@ void ref_pfsp_evaluate_range(const lb1_bound_data* d1, const lb2_bound_data* d2,
       }
     }
   }
+}
+void ref_pfsp_evaluate_range_rep(const lb1_bound_data* d1, const lb2_bound_data* d2, int lb, const Node* parents,
+                                 int begin, int end, int best, int* bounds, int repeat) {
+  for (int r = 0; r < repeat; r++) ref_pfsp_evaluate_range(d1, d2, lb, parents, begin, end, best, bounds);
 }
 #endif
