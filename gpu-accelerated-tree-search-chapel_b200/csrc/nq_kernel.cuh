@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NQ_THREADS) nq_evaluate_kernel(const uint8_t* 
   NqSmem<N>& sm = *reinterpret_cast<NqSmem<N>*>(smem_raw);
   run_tile_pipeline<NQ_STAGES, NQ_TILE, NQ_REC, N>(
       sm, parents, labels, count,
-      [](const uint8_t* in_tile, uint8_t* out_tile, int n) { nq_compute_tile<N, VAR>(in_tile, out_tile, n); });
+      [](const uint8_t* in_tile, uint8_t* out_tile, int n, long long) { nq_compute_tile<N, VAR>(in_tile, out_tile, n); });
 }
 
 }  // namespace tsb

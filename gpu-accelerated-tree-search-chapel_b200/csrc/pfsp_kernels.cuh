@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_lb1_kernel(const uint8_t* __r
   Lb1Smem& sm = *reinterpret_cast<Lb1Smem*>(smem_raw);
   stage_blob(&sm.tab, tables, sizeof(PfspLb1Tables), &sm.tab_bar);
   run_tile_pipeline<LB1_STAGES, PF_TILE, PF_REC, PF_MAXJ * 4>(
-      sm.tiles, parents, bounds, count, [&sm](const uint8_t* in_tile, uint8_t* out_tile, int n) {
+      sm.tiles, parents, bounds, count, [&sm](const uint8_t* in_tile, uint8_t* out_tile, int n, long long) {
         lb1_compute_tile<KIND, M>(sm, in_tile, out_tile, n);
       });
 }
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_lb2_kernel(const uint8_t* __r
   __syncthreads();
   mbar_wait(&sm.tab_bar[0], 0);
   run_tile_pipeline<LB2_STAGES, PF_TILE, PF_REC, PF_MAXJ * 4>(
-      sm.tiles, parents, bounds, count, [&sm, best](const uint8_t* in_tile, uint8_t* out_tile, int n) {
+      sm.tiles, parents, bounds, count, [&sm, best](const uint8_t* in_tile, uint8_t* out_tile, int n, long long) {
         lb2_compute_tile<M>(sm, in_tile, out_tile, n, best);
       });
 }

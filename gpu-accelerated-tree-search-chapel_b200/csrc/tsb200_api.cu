@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "nq_expand.cuh"
 #include "nq_kernel.cuh"
 #include "pfsp_kernels.cuh"
 #include "tsb200.h"
@@ -232,6 +233,18 @@ struct tsb_nq : Base {
   int variant = 0;  // env TSB200_NQ_VARIANT (kernel A/B experiments)
   int occ = 0;      // cached CTAs per SM
   bool attr_set = false;
+  // fused expand (evaluate + generate_children on the device) and the device-resident pool
+  uint8_t* d_cmask = nullptr;
+  int* d_tile = nullptr;
+  long long exp_cap = 0;  // parents the two arrays above are sized for
+  tsb::ExpandCounters* d_ctr = nullptr;
+  tsb::ExpandCounters* h_ctr = nullptr;  // pinned
+  uint8_t* d_children = nullptr;         // host-buffer expand: device image of the children
+  size_t d_children_bytes = 0;
+  bool exp_attr_set = false;
+  int occ_count = 0, occ_write = 0;
+  uint8_t* pool = nullptr;  // device-resident pool: `pool_size` nodes of 21 B, capacity `pool_cap`
+  long long pool_size = 0, pool_cap = 0;
 };
 
 namespace {
@@ -259,6 +272,76 @@ int launch_nq(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaS
 #define TSB_NQ_CASE(n) \
   case n:              \
     return launch_nq_n<n, 0>(h, in, out, count, s);
+    TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
+    TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
+    TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
+    TSB_NQ_CASE(20)
+#undef TSB_NQ_CASE
+  }
+  return TSB_EINVAL;
+}
+
+}  // namespace
+
+namespace {
+
+int nq_expand_reserve(tsb_nq* h, long long count) {
+  if (count > h->exp_cap) {
+    if (h->d_cmask) cudaFree(h->d_cmask);
+    if (h->d_tile) cudaFree(h->d_tile);
+    h->d_cmask = nullptr;
+    h->d_tile = nullptr;
+    h->exp_cap = 0;
+    const long long cap = std::max<long long>(count, h->M_max);
+    TSB_CUDA(cudaMalloc(&h->d_cmask, static_cast<size_t>(cap + tsb::NQ_TILE) * 4));
+    TSB_CUDA(cudaMalloc(&h->d_tile, static_cast<size_t>(cap / tsb::NQ_TILE + 4) * sizeof(int)));
+    h->exp_cap = cap;
+  }
+  if (!h->d_ctr) TSB_CUDA(cudaMalloc(&h->d_ctr, sizeof(tsb::ExpandCounters)));
+  if (!h->h_ctr) TSB_CUDA(cudaHostAlloc(&h->h_ctr, sizeof(tsb::ExpandCounters), cudaHostAllocPortable));
+  return TSB_OK;
+}
+
+// K1 + K2 + K3 on `s`; children_d may have any alignment; synchronous (the counts come back)
+template <int N>
+int nq_expand_n(tsb_nq* h, const uint8_t* parents_d, long long count, uint8_t* children_d, cudaStream_t s,
+                unsigned long long* n_children, unsigned long long* n_solutions) {
+  int rc = nq_expand_reserve(h, count);
+  if (rc != TSB_OK) return rc;
+  auto k1 = tsb::nq_expand_count_kernel<N>;
+  auto k3 = tsb::nq_expand_write_kernel<N>;
+  const size_t smem1 = sizeof(tsb::NqCountSmem<N>) + 128, smem3 = sizeof(tsb::NqWriteSmem) + 128;
+  if (!h->exp_attr_set) {
+    TSB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
+    TSB_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem3)));
+    h->exp_attr_set = true;
+  }
+  const long long tiles = (count + tsb::NQ_TILE - 1) / tsb::NQ_TILE;
+  int g1 = 1, g3 = 1;
+  rc = grid_for(k1, tsb::NQ_THREADS, smem1, count, tsb::NQ_TILE, h->di.sms, &g1, &h->occ_count);
+  if (rc != TSB_OK) return rc;
+  rc = grid_for(k3, tsb::NQ_THREADS, smem3, tiles * tsb::NQ_TILE, tsb::NQ_TILE, h->di.sms, &g3, &h->occ_write);
+  if (rc != TSB_OK) return rc;
+  TSB_CUDA(cudaMemsetAsync(h->d_ctr, 0, sizeof(tsb::ExpandCounters), s));
+  k1<<<g1, tsb::NQ_THREADS, smem1, s>>>(parents_d, h->d_cmask, count, h->d_tile, h->d_ctr);
+  tsb::scan_tiles_kernel<<<1, 1024, 0, s>>>(h->d_tile, static_cast<int>(tiles), h->d_ctr);
+  k3<<<g3, tsb::NQ_THREADS, smem3, s>>>(parents_d, reinterpret_cast<const uint32_t*>(h->d_cmask), h->d_tile, count,
+                                        children_d);
+  TSB_CUDA(cudaGetLastError());
+  h->launches += 3;
+  TSB_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(tsb::ExpandCounters), cudaMemcpyDeviceToHost, s));
+  TSB_CUDA(cudaStreamSynchronize(s));
+  *n_children = h->h_ctr->children;
+  *n_solutions = h->h_ctr->solutions;
+  return TSB_OK;
+}
+
+int nq_expand_dispatch(tsb_nq* h, const uint8_t* parents_d, long long count, uint8_t* children_d, cudaStream_t s,
+                       unsigned long long* nc, unsigned long long* ns) {
+  switch (h->N) {
+#define TSB_NQ_CASE(n) \
+  case n:              \
+    return nq_expand_n<n>(h, parents_d, count, children_d, s, nc, ns);
     TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
     TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
     TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
@@ -392,8 +475,138 @@ int tsb_nq_create(tsb_nq** out, int device, int N, int g, int M_max) {
 
 void tsb_nq_destroy(tsb_nq* h) {
   if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->d_cmask) cudaFree(h->d_cmask);
+  if (h->d_tile) cudaFree(h->d_tile);
+  if (h->d_ctr) cudaFree(h->d_ctr);
+  if (h->h_ctr) cudaFreeHost(h->h_ctr);
+  if (h->d_children) cudaFree(h->d_children);
+  if (h->pool) cudaFree(h->pool);
   h->fini();
   delete h;
+}
+
+// ---- fused evaluate + generate_children, and the device-resident pool
+int tsb_nq_expand_device(tsb_nq* h, const void* parents_d, int count, void* children_d, uint64_t* n_children,
+                         uint64_t* n_solutions, void* stream) {
+  if (!h || count < 0 || !n_children || !n_solutions) return TSB_EINVAL;
+  *n_children = *n_solutions = 0;
+  if (count == 0) return TSB_OK;
+  if (!parents_d || !children_d) return TSB_EINVAL;
+  if (reinterpret_cast<uintptr_t>(parents_d) & 15) return TSB_EALIGN;
+  TSB_CUDA(cudaSetDevice(h->device));
+  unsigned long long nc = 0, ns = 0;
+  int rc = nq_expand_dispatch(h, static_cast<const uint8_t*>(parents_d), count, static_cast<uint8_t*>(children_d),
+                              stream ? static_cast<cudaStream_t>(stream) : h->stream, &nc, &ns);
+  *n_children = nc;
+  *n_solutions = ns;
+  return rc;
+}
+
+int tsb_nq_expand(tsb_nq* h, const void* parents, int count, void* children, uint64_t capacity, uint64_t* n_children,
+                  uint64_t* n_solutions) {
+  if (!h || count < 0 || count > h->M_max || !n_children || !n_solutions) return TSB_EINVAL;
+  *n_children = *n_solutions = 0;
+  if (count == 0) return TSB_OK;
+  if (!parents || !children) return TSB_EINVAL;
+  TSB_CUDA(cudaSetDevice(h->device));
+  const size_t need = static_cast<size_t>(h->M_max) * h->N * sizeof(tsb_nq_node) + 64;
+  if (h->d_children_bytes < need) {
+    if (h->d_children) cudaFree(h->d_children);
+    h->d_children = nullptr;
+    h->d_children_bytes = 0;
+    TSB_CUDA(cudaMalloc(&h->d_children, need));
+    h->d_children_bytes = need;
+  }
+  const size_t in_b = sizeof(tsb_nq_node) * static_cast<size_t>(count);
+  const bool in_locked = h->reg.ensure(parents, in_b);
+  const void* src = parents;
+  if (!in_locked) {
+    int rc = h->ensure_staging();
+    if (rc != TSB_OK) return rc;
+    std::memcpy(h->h_in, parents, in_b);
+    src = h->h_in;
+  }
+  TSB_CUDA(cudaMemcpyAsync(h->d_in, src, in_b, cudaMemcpyHostToDevice, h->stream));
+  unsigned long long nc = 0, ns = 0;
+  int rc = nq_expand_dispatch(h, h->d_in, count, h->d_children, h->stream, &nc, &ns);
+  if (rc != TSB_OK) return rc;
+  *n_children = nc;
+  *n_solutions = ns;
+  if (nc > capacity) return TSB_ENOMEM;  // the caller's children array is too small; counts are valid
+  if (nc) TSB_CUDA(cudaMemcpy(children, h->d_children, nc * sizeof(tsb_nq_node), cudaMemcpyDeviceToHost));
+  return TSB_OK;
+}
+
+int tsb_nq_pool_push(tsb_nq* h, const void* nodes, int64_t n) {
+  if (!h || n < 0 || (n && !nodes)) return TSB_EINVAL;
+  TSB_CUDA(cudaSetDevice(h->device));
+  const long long need = h->pool_size + n;
+  if (need > h->pool_cap) {
+    const long long cap = std::max<long long>({need, 2 * h->pool_cap, 1LL << 20});
+    uint8_t* np = nullptr;
+    TSB_CUDA(cudaMalloc(&np, static_cast<size_t>(cap) * sizeof(tsb_nq_node) + 64));
+    if (h->pool_size)
+      TSB_CUDA(cudaMemcpy(np, h->pool, static_cast<size_t>(h->pool_size) * sizeof(tsb_nq_node), cudaMemcpyDeviceToDevice));
+    if (h->pool) cudaFree(h->pool);
+    h->pool = np;
+    h->pool_cap = cap;
+  }
+  if (n)
+    TSB_CUDA(cudaMemcpy(h->pool + h->pool_size * sizeof(tsb_nq_node), nodes, static_cast<size_t>(n) * sizeof(tsb_nq_node),
+                        cudaMemcpyHostToDevice));
+  h->pool_size = need;
+  return TSB_OK;
+}
+
+int64_t tsb_nq_pool_size(const tsb_nq* h) { return h ? h->pool_size : -1; }
+
+int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_children, uint64_t* n_solutions) {
+  if (!h || m < 1 || M < 1 || M > h->M_max || !n_parents || !n_children || !n_solutions) return TSB_EINVAL;
+  *n_parents = 0;
+  *n_children = *n_solutions = 0;
+  if (h->pool_size < m) return TSB_OK;  // popBackBulk returns 0 below m (lib/commons/Pool.chpl:50-59)
+  TSB_CUDA(cudaSetDevice(h->device));
+  const long long n = std::min<long long>(h->pool_size, M);
+  const long long base = h->pool_size - n;
+  // room for the worst case (every slot of every parent survives) before anything is overwritten
+  int rc = TSB_OK;
+  const long long worst = base + n * h->N;
+  if (worst > h->pool_cap) {
+    const long long keep = h->pool_size;
+    h->pool_size = worst;  // make tsb_nq_pool_push(.., 0) grow to `worst`
+    h->pool_size = keep;
+    const long long cap = std::max<long long>(worst, 2 * h->pool_cap);
+    uint8_t* np = nullptr;
+    TSB_CUDA(cudaMalloc(&np, static_cast<size_t>(cap) * sizeof(tsb_nq_node) + 64));
+    TSB_CUDA(cudaMemcpy(np, h->pool, static_cast<size_t>(keep) * sizeof(tsb_nq_node), cudaMemcpyDeviceToDevice));
+    cudaFree(h->pool);
+    h->pool = np;
+    h->pool_cap = cap;
+  }
+  // the newest n nodes become the chunk (order preserved); their children are appended where they were
+  TSB_CUDA(cudaMemcpyAsync(h->d_in, h->pool + base * sizeof(tsb_nq_node), static_cast<size_t>(n) * sizeof(tsb_nq_node),
+                           cudaMemcpyDeviceToDevice, h->stream));
+  unsigned long long nc = 0, ns = 0;
+  rc = nq_expand_dispatch(h, h->d_in, n, h->pool + base * sizeof(tsb_nq_node), h->stream, &nc, &ns);
+  if (rc != TSB_OK) return rc;
+  h->pool_size = base + static_cast<long long>(nc);
+  *n_parents = n;
+  *n_children = nc;
+  *n_solutions = ns;
+  return TSB_OK;
+}
+
+int tsb_nq_pool_drain(tsb_nq* h, void* nodes, int64_t capacity, int64_t* n) {
+  if (!h || !n || capacity < 0) return TSB_EINVAL;
+  *n = h->pool_size;
+  if (h->pool_size > capacity) return TSB_ENOMEM;
+  TSB_CUDA(cudaSetDevice(h->device));
+  if (h->pool_size)
+    TSB_CUDA(cudaMemcpy(nodes, h->pool, static_cast<size_t>(h->pool_size) * sizeof(tsb_nq_node), cudaMemcpyDeviceToHost));
+  h->pool_size = 0;
+  return TSB_OK;
 }
 
 int tsb_nq_evaluate(tsb_nq* h, const void* parents, int count, uint8_t* labels) {

@@ -462,6 +462,59 @@ int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out) {
   return TSB_OK;
 }
 
+int tsb_nq_search_device(int N, int g, int m, int M, tsb_search_stats* out) {
+  if (!out || N < 1 || N > TSB_MAX_QUEENS || g < 1 || m < 1 || M < 1) return TSB_EINVAL;
+  std::memset(out, 0, sizeof(*out));
+  if (int rc = tsb_init_devices(1); rc != TSB_OK) return rc;
+  Pool<tsb_nq_node> pool;
+  tsb_nq_node root{};
+  for (int i = 0; i < N; i++) root.board[i] = static_cast<uint8_t>(i);
+  pool.pushBack(root);
+  uint64_t tree = 0, sol = 0;
+  tsb_nq_node parent;
+  double t0 = now_s();
+  while (pool.size < static_cast<size_t>(m)) {  // step 1 on the CPU, as in the reference
+    if (!pool.popFront(parent)) break;
+    nq_decompose(N, parent, tree, sol, pool);
+  }
+  double t1 = now_s();
+  out->t_step1 = t1 - t0;
+  tsb_nq* h = nullptr;  // step 2: the pool moves to the device and stays there
+  int rc = tsb_nq_create(&h, 0, N, g, M);
+  if (rc != TSB_OK) return rc;
+  rc = tsb_nq_pool_push(h, &pool.el[pool.front], static_cast<int64_t>(pool.size));
+  pool.front = 0;
+  pool.size = 0;
+  while (rc == TSB_OK) {
+    int64_t np = 0;
+    uint64_t nc = 0, ns = 0;
+    rc = tsb_nq_pool_step(h, m, M, &np, &nc, &ns);
+    if (rc != TSB_OK || np == 0) break;
+    tree += nc;
+    sol += ns;
+    out->offloads += 1;
+    out->offloaded_parents += static_cast<uint64_t>(np);
+  }
+  if (rc == TSB_OK) {  // fewer than m nodes left: back to the host pool for step 3
+    const int64_t left = tsb_nq_pool_size(h);
+    std::vector<tsb_nq_node> rest(static_cast<size_t>(left) + 1);
+    int64_t n = 0;
+    rc = tsb_nq_pool_drain(h, rest.data(), left, &n);
+    for (int64_t i = 0; i < n && rc == TSB_OK; i++) pool.pushBack(rest[i]);
+  }
+  out->kernel_launches = tsb_nq_kernel_launches(h);
+  tsb_nq_destroy(h);
+  if (rc != TSB_OK) return rc;
+  out->per_gpu_tree[0] = tree;
+  double t2 = now_s();
+  out->t_step2 = t2 - t1;
+  while (pool.popBack(parent)) nq_decompose(N, parent, tree, sol, pool);  // step 3
+  out->t_step3 = now_s() - t2;
+  out->explored_tree = tree;
+  out->explored_sol = sol;
+  return TSB_OK;
+}
+
 int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out) {
   if (!out || lb_kind < 0 || lb_kind > 2 || (ub != 0 && ub != 1) || m < 1 || M < 1 || D < 1 || D > 8)
     return TSB_EINVAL;

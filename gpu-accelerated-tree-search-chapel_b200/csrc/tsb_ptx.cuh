@@ -105,7 +105,7 @@ __device__ __forceinline__ uint32_t shf_r_wrap(uint32_t lo, uint32_t hi, uint32_
 // __syncthreads per tile.  The last partial tile (count % TILE records) is done by the CTA
 // that owns it with plain word/byte copies (bulk copies need 16-B granularity).
 //
-// Functor: compute(const uint8_t* in_tile, uint8_t* out_tile, int records_in_tile)
+// Functor: compute(const uint8_t* in_tile, uint8_t* out_tile, int records_in_tile, long long tile_index)
 // ---------------------------------------------------------------------------------------------
 template <int STAGES, int IN_BYTES, int OUT_BYTES>
 struct TileSmem {
@@ -148,7 +148,7 @@ __device__ __forceinline__ void run_tile_pipeline(Smem& sm, const uint8_t* __res
     const uint32_t parity = static_cast<uint32_t>((it / STAGES) & 1);
     const long long tile = first + it * stride;
     mbar_wait(&sm.full[s], parity);
-    compute(sm.in[s], sm.out[s], TILE);
+    compute(sm.in[s], sm.out[s], TILE, tile);
     fence_async_smem();
     // the store issued from out[(s+1)%STAGES] STAGES-1 iterations ago must have drained its
     // shared-memory reads before anyone writes that buffer in the next iteration
@@ -181,7 +181,7 @@ __device__ __forceinline__ void run_tile_pipeline(Smem& sm, const uint8_t* __res
     const int in_b = rem * IN_REC, out_b = rem * OUT_REC;
     for (int i = tid; i < static_cast<int>(IN_BYTES); i += blockDim.x) sin[i] = i < in_b ? src[i] : 0;
     __syncthreads();
-    compute(sin, sout, rem);
+    compute(sin, sout, rem, full_tiles);
     __syncthreads();
     for (int i = tid; i < out_b; i += blockDim.x) dst[i] = sout[i];
   }

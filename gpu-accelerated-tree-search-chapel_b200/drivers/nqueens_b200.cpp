@@ -10,7 +10,7 @@
 #include "tsb200.h"
 
 int main(int argc, char** argv) {
-  int N = 14, g = 1, m = 25, M = 50000, D = 1;
+  int N = 14, g = 1, m = 25, M = 50000, D = 1, devpool = 0;
   for (int i = 1; i < argc; i++) {
     if (!std::strcmp(argv[i], "-h") || !std::strcmp(argv[i], "--help")) {
       std::printf("\n  General Parameters:\n\n   --m   int   minimum number of elements to offload on a GPU device\n"
@@ -23,7 +23,8 @@ int main(int argc, char** argv) {
     if (i + 1 >= argc) break;
     int* dst = !std::strcmp(argv[i], "--N") ? &N : !std::strcmp(argv[i], "--g") ? &g
              : !std::strcmp(argv[i], "--m") ? &m : !std::strcmp(argv[i], "--M") ? &M
-             : !std::strcmp(argv[i], "--D") ? &D : nullptr;
+             : !std::strcmp(argv[i], "--D") ? &D
+             : !std::strcmp(argv[i], "--devpool") ? &devpool : nullptr;  // 1: pool of step 2 resident on the GPU
     if (dst) *dst = std::atoi(argv[++i]);
   }
   if (N <= 0 || g <= 0 || m <= 0 || M <= 0 || D <= 0) {
@@ -34,7 +35,7 @@ int main(int argc, char** argv) {
               "Resolution of the %d-Queens instance\n  with %d safety check(s) per evaluation\n"
               "=================================================\n", D > 1 ? "Multi-GPU" : "Single-GPU", N, g);
   tsb_search_stats st;
-  const int rc = tsb_nq_search(N, g, m, M, D, &st);
+  const int rc = devpool ? tsb_nq_search_device(N, g, m, M, &st) : tsb_nq_search(N, g, m, M, D, &st);
   if (rc != TSB_OK) {
     std::fprintf(stderr, "tsb_nq_search: %s (%s)\n", tsb_strerror(rc), tsb_last_cuda_error());
     return 3;

@@ -61,6 +61,12 @@ SYMBOLS = {
     "tsb_nq_destroy": (None, [_vp]),
     "tsb_nq_evaluate": (_i, [_vp, _vp, _i, _vp]),
     "tsb_nq_evaluate_device": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "tsb_nq_expand": (_i, [_vp, _vp, _i, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
+    "tsb_nq_expand_device": (_i, [_vp, _vp, _i, _vp, C.POINTER(_u64), C.POINTER(_u64), _vp]),
+    "tsb_nq_pool_push": (_i, [_vp, _vp, _i64]),
+    "tsb_nq_pool_size": (_i64, [_vp]),
+    "tsb_nq_pool_step": (_i, [_vp, _i, _i, C.POINTER(_i64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "tsb_nq_pool_drain": (_i, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "tsb_nq_set_xfer": (_i, [_vp, _i]),
     "tsb_nq_kernel_launches": (_u64, [_vp]),
     "tsb_pfsp_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _pi32, _pi32, _pi32, _i, _pi32, _pi32, _pi32, _pi32, _pi32]),
@@ -75,6 +81,7 @@ SYMBOLS = {
     "tsb_pfsp_tables_build": (_i, [C.POINTER(PfspTables), _i]),
     "tsb_pfsp_create_from_tables": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(PfspTables)]),
     "tsb_nq_search": (_i, [_i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
+    "tsb_nq_search_device": (_i, [_i, _i, _i, _i, C.POINTER(SearchStats)]),
     "tsb_pfsp_search": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
 }
 

@@ -56,6 +56,45 @@ class NQueensEvaluator:
         self.evaluate_gpu(parents, parents.shape[0] * self.N, labels)
         return labels
 
+    # ---- beyond the drop-in: fused evaluate_gpu + generate_children, device-resident pool
+    def expand(self, parents: np.ndarray):
+        """children of the chunk (packed, reference order) and the number of depth == N parents:
+        evaluate_gpu (nqueens_gpu_chpl.chpl:97-123) + generate_children (:126-149) in one device pass"""
+        assert parents.dtype == NQ_NODE_DTYPE and parents.flags.c_contiguous
+        cap = parents.shape[0] * self.N
+        out = np.empty(max(cap, 1), dtype=NQ_NODE_DTYPE)
+        nc, ns = C.c_uint64(0), C.c_uint64(0)
+        check(lib().tsb_nq_expand(self._h, parents.ctypes.data, parents.shape[0], out.ctypes.data, cap,
+                                  C.byref(nc), C.byref(ns)), "tsb_nq_expand")
+        return out[: nc.value].copy(), int(ns.value)
+
+    def expand_device(self, parents_ptr: int, count: int, children_ptr: int, stream: int = 0):
+        nc, ns = C.c_uint64(0), C.c_uint64(0)
+        check(lib().tsb_nq_expand_device(self._h, parents_ptr, count, children_ptr, C.byref(nc), C.byref(ns), stream),
+              "tsb_nq_expand_device")
+        return int(nc.value), int(ns.value)
+
+    def pool_push(self, nodes: np.ndarray) -> None:
+        assert nodes.dtype == NQ_NODE_DTYPE and nodes.flags.c_contiguous
+        check(lib().tsb_nq_pool_push(self._h, nodes.ctypes.data, nodes.shape[0]), "tsb_nq_pool_push")
+
+    @property
+    def pool_size(self) -> int:
+        return int(lib().tsb_nq_pool_size(self._h))
+
+    def pool_step(self, m: int, M: int):
+        """(parents popped, children appended, solutions) of one device-side offload round"""
+        np_, nc, ns = C.c_int64(0), C.c_uint64(0), C.c_uint64(0)
+        check(lib().tsb_nq_pool_step(self._h, m, M, C.byref(np_), C.byref(nc), C.byref(ns)), "tsb_nq_pool_step")
+        return int(np_.value), int(nc.value), int(ns.value)
+
+    def pool_drain(self) -> np.ndarray:
+        n = self.pool_size
+        out = np.empty(max(n, 1), dtype=NQ_NODE_DTYPE)
+        got = C.c_int64(0)
+        check(lib().tsb_nq_pool_drain(self._h, out.ctypes.data, n, C.byref(got)), "tsb_nq_pool_drain")
+        return out[: got.value].copy()
+
     def evaluate_device(self, parents_ptr: int, count: int, labels_ptr: int, stream: int = 0) -> None:
         """device-resident form; pointers are raw device addresses (e.g. torch.Tensor.data_ptr())"""
         check(lib().tsb_nq_evaluate_device(self._h, parents_ptr, count, labels_ptr, stream), "tsb_nq_evaluate_device")
@@ -66,4 +105,11 @@ def nqueens_search(N: int = 14, g: int = 1, m: int = 25, M: int = 50000, D: int 
     (static split, D GPUs), run by the C++ emulation driver inside libtsb200.so"""
     st = SearchStats()
     check(lib().tsb_nq_search(N, g, m, M, D, C.byref(st)), "tsb_nq_search")
+    return st
+
+
+def nqueens_search_device(N: int = 14, g: int = 1, m: int = 25, M: int = 50000) -> SearchStats:
+    """same 3-step search, the pool of step 2 resident on the device (tsb_nq_pool_*)"""
+    st = SearchStats()
+    check(lib().tsb_nq_search_device(N, g, m, M, C.byref(st)), "tsb_nq_search_device")
     return st

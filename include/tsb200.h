@@ -100,6 +100,26 @@ int tsb_nq_evaluate(tsb_nq* h, const void* parents, int count, uint8_t* labels);
  * stream).  count is not limited by M_max. */
 int tsb_nq_evaluate_device(tsb_nq* h, const void* parents_d, int count, uint8_t* labels_d, void* stream);
 
+/* ---- beyond the drop-in: fused evaluate + generate_children on the device ----
+ * evaluate_gpu (nqueens_gpu_chpl.chpl:97-123) followed by generate_children (:126-149) in one call: the
+ * children of the chunk come back packed, in the reference's order (parents in order, slots j ascending);
+ * *n_solutions = parents with depth == N.  `children` must hold count*N nodes in the worst case; if it is
+ * smaller than the actual number, TSB_ENOMEM is returned with the counts set.  Synchronous. */
+int tsb_nq_expand(tsb_nq* h, const void* parents, int count, void* children, uint64_t capacity_nodes,
+                  uint64_t* n_children, uint64_t* n_solutions);
+int tsb_nq_expand_device(tsb_nq* h, const void* parents_d /*16-B aligned*/, int count,
+                         void* children_d /*any alignment*/, uint64_t* n_children, uint64_t* n_solutions,
+                         void* stream);
+
+/* ---- device-resident pool: the reference's SinglePool (lib/commons/Pool.chpl) kept in
+ * HBM.  push = pushBack of host nodes; step = one offload round of nqueens_gpu_chpl.chpl:197-215 done
+ * entirely on the device: popBackBulk(m, M) (nothing below m, else the newest min(size, M) nodes, order
+ * preserved), evaluate, generate_children appended to the pool; drain = move what is left to the host. */
+int tsb_nq_pool_push(tsb_nq* h, const void* nodes, int64_t n);
+int64_t tsb_nq_pool_size(const tsb_nq* h);
+int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_children, uint64_t* n_solutions);
+int tsb_nq_pool_drain(tsb_nq* h, void* nodes, int64_t capacity_nodes, int64_t* n);
+
 int tsb_nq_set_xfer(tsb_nq* h, int mode);
 uint64_t tsb_nq_kernel_launches(const tsb_nq* h); /* kernels launched through this handle so far */
 
@@ -165,6 +185,9 @@ typedef struct {
 
 /* nqueens_gpu_chpl.chpl:152-248 / nqueens_multigpu_chpl.chpl:158-352 */
 int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out);
+/* the same 3-step search with the pool of step 2 resident on the device (tsb_nq_pool_*): identical chunk
+ * sequence, identical counts; the host only reads three counters per round.  D = 1. */
+int tsb_nq_search_device(int N, int g, int m, int M, tsb_search_stats* out);
 /* pfsp_gpu_chpl.chpl:306-431 / pfsp_multigpu_chpl.chpl:316-560 */
 int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out);
 

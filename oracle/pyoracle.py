@@ -91,6 +91,8 @@ def lib() -> C.CDLL:
         L.or_nq_evaluate_range.argtypes = [vp, i32, i32, i32, i32, vp]
         L.or_pfsp_evaluate.argtypes = [C.POINTER(Tables), i32, vp, i32, i64, vp]
         L.or_pfsp_evaluate_range.argtypes = [C.POINTER(Tables), i32, vp, i32, i32, i64, vp]
+        L.or_nq_expand_chunk.argtypes = [vp, i32, i32, i32, vp, i64, C.POINTER(C.c_uint64)]
+        L.or_nq_expand_chunk.restype = C.c_int64
         L.or_nq_search_seq.argtypes = [i32, i32, C.POINTER(SearchResult)]
         L.or_nq_search_offload.argtypes = [i32, i32, i32, i32, i32, C.POINTER(SearchResult)]
         L.or_pfsp_search_seq.argtypes = [i32, i32, i32, i32, C.POINTER(SearchResult)]
@@ -128,6 +130,16 @@ def pfsp_evaluate(t: Tables, lb_kind: int, parents: np.ndarray, best: int, fill:
     bounds = np.full(parents.shape[0] * t.jobs, fill, dtype=np.int32)
     lib().or_pfsp_evaluate(C.byref(t), lb_kind, _ptr(parents), parents.shape[0], int(best), _ptr(bounds))
     return bounds
+
+
+def nq_expand(parents: np.ndarray, N: int, g: int = 1):
+    """(children, n_solutions) of one chunk in the reference's generate_children order"""
+    assert parents.dtype == NQ_NODE_DTYPE and parents.flags.c_contiguous
+    cap = parents.shape[0] * N + 1
+    out = np.zeros(cap, dtype=NQ_NODE_DTYPE)
+    sol = C.c_uint64(0)
+    n = lib().or_nq_expand_chunk(_ptr(parents), parents.shape[0], N, g, _ptr(out), cap, C.byref(sol))
+    return out[:n].copy(), int(sol.value)
 
 
 def nq_live_mask(parents: np.ndarray, N: int) -> np.ndarray:

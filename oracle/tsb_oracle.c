@@ -542,6 +542,25 @@ static void nq_generate_children(int N, const or_nq_node* parents, int64_t size,
   }
 }
 
+/* evaluate_gpu + generate_children of one chunk (nqueens_gpu_chpl.chpl:97-149): the children, in the
+ * reference's order, as they would be appended to the pool */
+int64_t or_nq_expand_chunk(const or_nq_node* parents, int count, int N, int g, or_nq_node* children,
+                           int64_t capacity, uint64_t* solutions) {
+  uint8_t* labels = (uint8_t*)malloc((size_t)count * N + 1);
+  or_pool pool;
+  pool_init(&pool, sizeof(or_nq_node));
+  uint64_t tree = 0, sol = 0;
+  memset(labels, 0xCD, (size_t)count * N + 1);
+  or_nq_evaluate(parents, count, N, g, labels);
+  nq_generate_children(N, parents, count, labels, &tree, &sol, &pool);
+  const int64_t n = pool.size;
+  if (n <= capacity) memcpy(children, pool.elements + (size_t)pool.front * pool.elt, (size_t)n * sizeof(or_nq_node));
+  if (solutions) *solutions = sol;
+  pool_free(&pool);
+  free(labels);
+  return n;
+}
+
 /* offload loop of one pool: nqueens_gpu_chpl.chpl:197-215; capture hook for tests */
 typedef struct {
   int which;

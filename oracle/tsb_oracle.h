@@ -80,6 +80,11 @@ void or_nq_evaluate_range(const or_nq_node* parents, int begin, int end, int N, 
 void or_pfsp_evaluate_range(const or_pfsp_tables* t, int lb_kind, const or_pfsp_node* parents, int begin,
                             int end, int64_t best, int32_t* bounds);
 
+/* evaluate_gpu + generate_children of one chunk (nqueens_gpu_chpl.chpl:97-149): children in the reference's
+ * order; returns their number (children filled only if it fits `capacity`) */
+int64_t or_nq_expand_chunk(const or_nq_node* parents, int count, int N, int g, or_nq_node* children,
+                           int64_t capacity, uint64_t* solutions);
+
 /* ---- whole searches ---- */
 typedef struct {
   uint64_t tree, sol;

@@ -1,0 +1,83 @@
+"""GPU tests of the fused evaluate + generate_children path and of the device-resident pool:
+children arrays byte-identical to the oracle's generate_children output, pools byte-identical after the same
+rounds, and whole searches with the reference's counts."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import tsb200
+from oracle import pyoracle as po
+from test_gpu_parity import rand_nq
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N", [1, 4, 8, 13, 17, 19, 20])
+def test_expand_matches_oracle_children(N):
+    rng = np.random.default_rng(500 + N)
+    with tsb200.NQueensEvaluator(N, M=20000) as ev:
+        for count, lo in ((1, 0), (3, 0), (511, 0), (512, 0), (513, 2), (4096 + 17, 0), (20000, max(0, N - 6))):
+            parents = rand_nq(rng, N, count, depth_lo=lo)
+            got, gsol = ev.expand(parents)
+            want, wsol = po.nq_expand(parents.view(po.NQ_NODE_DTYPE), N)
+            assert gsol == wsol and got.shape[0] == want.shape[0]
+            assert got.tobytes() == want.tobytes()
+
+
+def test_expand_dense_tiles_take_the_unstaged_path():
+    """depth 0/1 parents have up to N children each: far more than a tile's staging image holds"""
+    N = 17
+    rng = np.random.default_rng(9)
+    parents = rand_nq(rng, N, 3000, depth_lo=0, depth_hi=1)
+    with tsb200.NQueensEvaluator(N, M=3000) as ev:
+        got, gsol = ev.expand(parents)
+    want, wsol = po.nq_expand(parents.view(po.NQ_NODE_DTYPE), N)
+    assert gsol == wsol == 0 and got.tobytes() == want.tobytes() and got.shape[0] > 3000 * 10
+
+
+@pytest.mark.parametrize("N,which", [(12, 3), (14, 100)])
+def test_expand_on_captured_real_chunks(N, which):
+    parents = po.nq_capture_chunk(N, which).view(tsb200.NQ_NODE_DTYPE)
+    with tsb200.NQueensEvaluator(N, M=50000) as ev:
+        got, gsol = ev.expand(parents)
+    want, wsol = po.nq_expand(parents.view(po.NQ_NODE_DTYPE), N)
+    assert gsol == wsol and got.tobytes() == want.tobytes()
+
+
+def test_device_pool_is_byte_identical_to_the_reference_pool():
+    """run the reference's offload loop (popBackBulk(m, M) -> evaluate -> generate_children -> pushBack) on the
+    host with the oracle and on the device with tsb_nq_pool_*; the pools must agree after every round"""
+    N, m, M = 11, 25, 700
+    rng = np.random.default_rng(4)
+    start = rand_nq(rng, N, 60, depth_lo=1, depth_hi=3)
+    host = [start[i:i + 1] for i in range(start.shape[0])]
+    host_pool = start.copy()
+    with tsb200.NQueensEvaluator(N, M=M) as ev:
+        ev.pool_push(start)
+        for _ in range(40):
+            n_par, n_child, n_sol = ev.pool_step(m, M)
+            if host_pool.shape[0] < m:
+                assert n_par == 0
+                break
+            n = min(host_pool.shape[0], M)
+            chunk = np.ascontiguousarray(host_pool[host_pool.shape[0] - n:])
+            kids, sol = po.nq_expand(chunk.view(po.NQ_NODE_DTYPE), N)
+            host_pool = np.concatenate([host_pool[: host_pool.shape[0] - n], kids.view(tsb200.NQ_NODE_DTYPE)])
+            assert (n_par, n_child, n_sol) == (n, kids.shape[0], sol)
+            assert ev.pool_size == host_pool.shape[0]
+        rest = ev.pool_drain()
+        assert rest.tobytes() == np.ascontiguousarray(host_pool).tobytes() and ev.pool_size == 0
+    del host
+
+
+@pytest.mark.parametrize("N,m,M", [(10, 25, 50000), (12, 25, 50000), (12, 5, 300), (13, 25, 4096), (14, 25, 50000),
+                                   (15, 25, 1 << 20)])
+def test_device_resident_search_counts(golden_dir, N, m, M):
+    counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
+    st = tsb200.nqueens_search_device(N, 1, m, M)
+    assert (st.explored_tree, st.explored_sol) == (counts["tree"], counts["sol"])
+    ref = po.nq_search_offload(N, 1, m, M, 1)  # same chunk sequence as the reference driver
+    assert (st.offloads, st.offloaded_parents) == (ref.offloads, ref.offloaded_parents)
+    assert st.kernel_launches == 3 * st.offloads
