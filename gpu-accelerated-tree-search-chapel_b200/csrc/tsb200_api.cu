@@ -544,7 +544,8 @@ int tsb_nq_pool_push(tsb_nq* h, const void* nodes, int64_t n) {
   TSB_CUDA(cudaSetDevice(h->device));
   const long long need = h->pool_size + n;
   if (need > h->pool_cap) {
-    const long long cap = std::max<long long>({need, 2 * h->pool_cap, 1LL << 20});
+    // room for two worst-case rounds up front, so that growth (a device-wide realloc + copy) stays rare
+    const long long cap = std::max<long long>({need, 2 * h->pool_cap, 1LL << 20, 2LL * h->M_max * h->N});
     uint8_t* np = nullptr;
     TSB_CUDA(cudaMalloc(&np, static_cast<size_t>(cap) * sizeof(tsb_nq_node) + 64));
     if (h->pool_size)
@@ -575,8 +576,6 @@ int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_ch
   const long long worst = base + n * h->N;
   if (worst > h->pool_cap) {
     const long long keep = h->pool_size;
-    h->pool_size = worst;  // make tsb_nq_pool_push(.., 0) grow to `worst`
-    h->pool_size = keep;
     const long long cap = std::max<long long>(worst, 2 * h->pool_cap);
     uint8_t* np = nullptr;
     TSB_CUDA(cudaMalloc(&np, static_cast<size_t>(cap) * sizeof(tsb_nq_node) + 64));

@@ -19,7 +19,7 @@ def test_expand_matches_oracle_children(N):
     rng = np.random.default_rng(500 + N)
     with tsb200.NQueensEvaluator(N, M=20000) as ev:
         for count, lo in ((1, 0), (3, 0), (511, 0), (512, 0), (513, 2), (4096 + 17, 0), (20000, max(0, N - 6))):
-            parents = rand_nq(rng, N, count, depth_lo=lo)
+            parents = rand_nq(rng, N, count, depth_lo=min(lo, N))
             got, gsol = ev.expand(parents)
             want, wsol = po.nq_expand(parents.view(po.NQ_NODE_DTYPE), N)
             assert gsol == wsol and got.shape[0] == want.shape[0]
