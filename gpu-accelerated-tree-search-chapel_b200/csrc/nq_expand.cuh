@@ -1,4 +1,4 @@
-// nq_expand.cuh — fused N-Queens evaluation + child generation on the device.
+// nq_expand.cuh — N-Queens evaluation + child generation on the device.
 //
 // Restates, on the GPU, evaluate_gpu (nqueens_gpu_chpl.chpl:97-123) followed by generate_children
 // (:126-149): for every parent p of a chunk, in order, and every slot j = depth..N-1, in order, whose
@@ -6,26 +6,25 @@
 // depth == N counts as one explored solution.  The children come out PACKED and IN THE REFERENCE'S
 // ORDER, so a pool that appends them is byte-identical to the reference's pool after the same round.
 //
-// Three kernels per chunk:
-//   K1 nq_expand_count : the evaluator of nq_kernel.cuh, but instead of N label bytes per parent it
-//                        writes one 32-bit child mask (bit j <=> child j exists) and per-tile totals
-//   K2 scan_tiles      : exclusive scan of the per-tile child counts (one CTA)
-//   K3 nq_expand_write : per tile, exclusive scan of the per-parent counts, children built in shared
-//                        memory as a contiguous byte image and written with one TMA bulk store plus
-//                        < 16 head / tail bytes (21-byte records land at arbitrary alignment)
+// Three kernels per chunk (expand_common.cuh), the chunk read in place from the pool arena:
+//   nq_expand_count : the evaluator of nq_kernel.cuh (TMA-pipelined tiles of 512 parents), but instead of N
+//                     label bytes per parent it writes one 32-bit child mask (bit j <=> child j exists) and
+//                     one child count per tile; parents with depth == N are counted as solutions
+//   nq_expand_build : tile counts -> offsets of the CTA's own tiles (prologue); per tile (2-stage TMA prefetch
+//                     of parents + masks): block scan of the per-parent counts, children built in shared
+//                     memory as a contiguous byte image at the 16-byte phase of their destination — one thread
+//                     per child, the parent read as six aligned words, the two queens swapped by an XOR patch
+//                     in registers, realigned by funnel shifts and stored as words (+ the few bytes of the two
+//                     words it shares with its neighbours) — and written with one TMA bulk store plus < 16
+//                     head / tail bytes (21-byte records land at any alignment)
+// HBM traffic per parent: 21 B + 4 B (count) and 21 B (mostly L2) + 4 B + 21 B per child (build).
 #pragma once
+#include "expand_common.cuh"
 #include "nq_kernel.cuh"
 
 namespace tsb {
 
-struct ExpandCounters {
-  unsigned long long children;   // total children of the chunk (written by K2)
-  unsigned long long solutions;  // parents with depth == N (accumulated by K1)
-};
-
-// ------------------------------------------------------------------------------------------- K1
-template <int N>
-using NqCountSmem = TileSmem<NQ_STAGES, NQ_TILE * NQ_REC, NQ_TILE * 4>;
+constexpr int EXP_CAP = 1024;  // children per pass of the shared staging image (a tile averages ~512; denser tiles take several passes)
 
 template <int N, int Q>
 __device__ __forceinline__ uint32_t nq_child_mask(NqParent<N, Q, 0>& p) {
@@ -36,13 +35,13 @@ __device__ __forceinline__ uint32_t nq_child_mask(NqParent<N, Q, 0>& p) {
     const uint32_t x = shf_r_wrap(S, 0u, p.amt[k]) & 1u;  // bit board[k] of the safe-value mask
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(cm) : "r"(x), "r"(1u << k));  // cm |= x << k on the FMA pipe
   }
-  return cm & shl_clamp(0xFFFFFFFFu, p.depth);  // only slots k >= depth exist; depth >= 32 cannot occur
+  return cm & shl_clamp(0xFFFFFFFFu, p.depth);  // only slots k >= depth exist
 }
 
+// evaluate the four parents of this thread: child masks + number of leaves (depth == N)
 template <int N>
-__device__ __forceinline__ void nq_count_tile(const uint8_t* in_tile, uint8_t* out_tile, int records, long long tile,
-                                              int* __restrict__ tile_sums, ExpandCounters* __restrict__ ctr,
-                                              int* red /* shared, 8 ints */) {
+__device__ __forceinline__ void nq_eval_quad(const uint8_t* in_tile, long long pos0, long long lo, long long hi,
+                                             uint32_t (&cm)[4], int& leaves) {
   const int t = threadIdx.x;
   const uint32_t* in_w = reinterpret_cast<const uint32_t*>(in_tile) + 21 * t;
   uint32_t w[21];
@@ -56,7 +55,16 @@ __device__ __forceinline__ void nq_count_tile(const uint8_t* in_tile, uint8_t* o
   p1.init(w);
   p2.init(w);
   p3.init(w);
-  const uint32_t dmax = max(max(p0.depth, p1.depth), max(p2.depth, p3.depth));
+  const uint32_t dep[4] = {p0.depth, p1.depth, p2.depth, p3.depth};
+  bool valid[4];
+  uint32_t dmax = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const long long p = pos0 + 4 * t + q;
+    valid[q] = p >= lo && p < hi;
+    if (valid[q]) dmax = max(dmax, dep[q]);  // records outside the chunk hold arbitrary bytes
+  }
+  dmax = min(dmax, 20u);
 #pragma unroll
   for (int j = 0; j < (N + 3) / 4; j++) {
     if (dmax > 4u * j) {
@@ -73,132 +81,225 @@ __device__ __forceinline__ void nq_count_tile(const uint8_t* in_tile, uint8_t* o
       }
     }
   }
-  uint32_t cm[4] = {nq_child_mask<N, 0>(p0), nq_child_mask<N, 1>(p1), nq_child_mask<N, 2>(p2),
-                    nq_child_mask<N, 3>(p3)};
-  const uint32_t dep[4] = {p0.depth, p1.depth, p2.depth, p3.depth};
-  int cnt = 0, leaves = 0;
+  cm[0] = nq_child_mask<N, 0>(p0);
+  cm[1] = nq_child_mask<N, 1>(p1);
+  cm[2] = nq_child_mask<N, 2>(p2);
+  cm[3] = nq_child_mask<N, 3>(p3);
+  leaves = 0;
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    const bool valid = 4 * t + q < records;
-    if (!valid || dep[q] >= (uint32_t)N) cm[q] = 0;
-    if (valid && dep[q] == (uint32_t)N) leaves++;
-    cnt += __popc(cm[q]);
-  }
-  reinterpret_cast<uint4*>(out_tile)[t] = make_uint4(cm[0], cm[1], cm[2], cm[3]);
-  // tile totals: warp shuffle reduction, then 4 warps through shared memory
-  int packed = cnt | (leaves << 20);  // cnt <= 512*20 < 2^20
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
-  __syncthreads();  // `red` may still be read by the previous tile's thread 0
-  if ((t & 31) == 0) red[t >> 5] = packed;
-  __syncthreads();
-  if (t == 0) {
-    const int tot = red[0] + red[1] + red[2] + red[3];
-    tile_sums[tile] = tot & 0xFFFFF;
-    if (tot >> 20) atomicAdd(&ctr->solutions, static_cast<unsigned long long>(tot >> 20));
+    if (!valid[q] || dep[q] >= static_cast<uint32_t>(N)) cm[q] = 0;
+    if (valid[q] && dep[q] == static_cast<uint32_t>(N)) leaves++;
   }
 }
 
-template <int N>
-__global__ void __launch_bounds__(NQ_THREADS) nq_expand_count_kernel(const uint8_t* __restrict__ parents,
-                                                                    uint8_t* __restrict__ cmask, long long count,
-                                                                    int* __restrict__ tile_sums,
-                                                                    ExpandCounters* __restrict__ ctr) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  NqCountSmem<N>& sm = *reinterpret_cast<NqCountSmem<N>*>(smem_raw);
-  __shared__ int red[8];
-  run_tile_pipeline<NQ_STAGES, NQ_TILE, NQ_REC, 4>(
-      sm, parents, cmask, count, [&](const uint8_t* in_tile, uint8_t* out_tile, int n, long long tile) {
-        nq_count_tile<N>(in_tile, out_tile, n, tile, tile_sums, ctr, red);
-      });
-}
-
-// ------------------------------------------------------------------------------------------- K2
-// exclusive scan of n ints in place (n <= a few 10^4), total into ctr->children; one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(int* __restrict__ v, int n, ExpandCounters* __restrict__ ctr) {
-  __shared__ int warp_tot[32];
-  __shared__ long long carry_s;
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  if (t == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + t;
-    const int x = i < n ? v[i] : 0;
-    int incl = x;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    if (lane == 31) warp_tot[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      int wt = warp_tot[lane], wi = wt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-        if (lane >= o) wi += y;
-      }
-      warp_tot[lane] = wi - wt;  // exclusive prefix of the warp totals
-    }
-    __syncthreads();
-    const long long carry = carry_s;
-    // child offsets of one chunk fit in 32 bits only up to 2^31 children; chunks are capped accordingly
-    if (i < n) v[i] = static_cast<int>(carry + warp_tot[wid] + incl - x);
-    __syncthreads();
-    if (t == 1023) carry_s = carry + warp_tot[wid] + incl;
-    __syncthreads();
-  }
-  if (t == 0) ctr->children = static_cast<unsigned long long>(carry_s);
-}
-
-// ------------------------------------------------------------------------------------------- K3
-constexpr int EXP_CAP = 1536;  // children of one tile that fit the shared staging image (average is ~512)
-
-struct NqWriteSmem {
-  alignas(128) uint8_t in[NQ_TILE * NQ_REC];
-  alignas(128) uint8_t stage[EXP_CAP * NQ_REC + 32];
-  alignas(8) uint64_t full;
+// ------------------------------------------------------------------------------------------- count
+struct NqCountSmem {
+  alignas(128) uint8_t in[2][NQ_TILE * NQ_REC];
+  alignas(8) uint64_t full[2];
   int warp_tot[4];
 };
 
 template <int N>
-__global__ void __launch_bounds__(NQ_THREADS) nq_expand_write_kernel(const uint8_t* __restrict__ parents,
-                                                                    const uint32_t* __restrict__ cmask,
-                                                                    const int* __restrict__ tile_off,
-                                                                    long long count, uint8_t* __restrict__ children) {
+__global__ void __launch_bounds__(NQ_THREADS) nq_expand_count_kernel(const uint8_t* __restrict__ arena,
+                                                                    const __grid_constant__ ExpandParams prm,
+                                                                    uint32_t* __restrict__ cmask,
+                                                                    int* __restrict__ tile_sums,
+                                                                    ExpandState* __restrict__ st) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  NqWriteSmem& sm = *reinterpret_cast<NqWriteSmem*>(smem_raw);
+  NqCountSmem& sm = *reinterpret_cast<NqCountSmem*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const long long tiles = (count + NQ_TILE - 1) / NQ_TILE;
+  constexpr uint32_t IN_BYTES = NQ_TILE * NQ_REC;
+  const int first = blockIdx.x, stride = gridDim.x;
   if (t == 0) {
-    mbar_init(&sm.full, 1);
+    mbar_init(&sm.full[0], 1);
+    mbar_init(&sm.full[1], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  uint32_t phase = 0;
-  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const long long first = tile * NQ_TILE;
-    const int records = static_cast<int>(count - first < NQ_TILE ? count - first : NQ_TILE);
-    // ---- stage the parents of this tile
-    if (records == NQ_TILE) {
-      if (t == 0) {
-        mbar_arrive_expect_tx(&sm.full, NQ_TILE * NQ_REC);
-        bulk_g2s(sm.in, parents + first * NQ_REC, NQ_TILE * NQ_REC, &sm.full);
-      }
-      mbar_wait(&sm.full, phase);
-      phase ^= 1;
-    } else {
-      for (int i = t; i < records * NQ_REC; i += NQ_THREADS) sm.in[i] = parents[first * NQ_REC + i];
-      __syncthreads();
-    }
-    // ---- per-parent counts and their exclusive scan over the tile (4 parents per thread, in order)
-    uint4 cmv = make_uint4(0, 0, 0, 0);
-    if (4 * t < records) cmv = reinterpret_cast<const uint4*>(cmask + first)[t];  // zero beyond `records` (K1)
-    uint32_t cm[4] = {cmv.x, cmv.y, cmv.z, cmv.w};
+  auto issue = [&](int lin, int s) {  // thread 0
+    long long at, lo, hi;
+    piece_of(prm, lin, NQ_TILE, at, lo, hi);
+    const uint32_t nb = tile_load_bytes(at, hi, NQ_TILE, NQ_REC);
+    mbar_arrive_expect_tx(&sm.full[s], nb);
+    bulk_g2s(sm.in[s], arena + at * IN_BYTES, nb, &sm.full[s]);  // default L2 policy: the build kernel re-reads it
+  };
+  if (t == 0) {
+    if (first < prm.n_tiles) issue(first, 0);
+    if (first + stride < prm.n_tiles) issue(first + stride, 1);
+  }
+  unsigned my_solutions = 0;
+  unsigned it = 0;
+  for (int lin = first; lin < prm.n_tiles; lin += stride, it++) {
+    const int s = it & 1;
+    long long at, lo, hi;
+    piece_of(prm, lin, NQ_TILE, at, lo, hi);
+    mbar_wait(&sm.full[s], (it >> 1) & 1u);
+    uint32_t cm[4];
+    int leaves;
+    nq_eval_quad<N>(sm.in[s], at * NQ_TILE, lo, hi, cm, leaves);
+    reinterpret_cast<uint4*>(cmask)[static_cast<long long>(lin) * (NQ_TILE / 4) + t] =
+        make_uint4(cm[0], cm[1], cm[2], cm[3]);
+    int packed = (__popc(cm[0]) + __popc(cm[1]) + __popc(cm[2]) + __popc(cm[3])) | (leaves << 20);
 #pragma unroll
-    for (int q = 0; q < 4; q++)
-      if (4 * t + q >= records) cm[q] = 0;  // entries past the chunk's end were never written by K1
+    for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
+    if (lane == 0) sm.warp_tot[wid] = packed;
+    __syncthreads();  // everyone is done with in[s]; warp totals visible
+    if (t == 0) {
+      const int tot = sm.warp_tot[0] + sm.warp_tot[1] + sm.warp_tot[2] + sm.warp_tot[3];
+      tile_sums[lin] = tot & 0xFFFFF;  // children of a tile <= 512*20 < 2^20
+      my_solutions += static_cast<unsigned>(tot >> 20);
+      if (lin + 2 * stride < prm.n_tiles) issue(lin + 2 * stride, s);
+    }
+    __syncthreads();  // warp_tot free for the next tile
+  }
+  if (t == 0 && my_solutions) atomicAdd(&st->solutions, static_cast<unsigned long long>(my_solutions));
+}
+
+// ------------------------------------------------------------------------------------------- build
+struct NqBuildSmem {
+  alignas(128) uint8_t in[2][NQ_TILE * NQ_REC];
+  alignas(128) uint32_t mask[2][NQ_TILE];
+  alignas(128) uint8_t stage[EXP_CAP * NQ_REC + 32];
+  alignas(8) uint64_t full[2];
+  uint16_t item[EXP_CAP];  // (record << 5) | slot, in child order
+  int warp_tot[4];
+  ScanSmem scan;
+};
+
+// child `c` of the tile -> bytes [B, B + 21) of the staging image (B = image offset of the child).  The parent
+// record sits at byte 21*r of the tile, i.e. at byte (r & 3) of an aligned word.
+__device__ __forceinline__ void nq_build_child(const uint8_t* in_tile, int item, uint8_t* image, int B) {
+  const int r = item >> 5, k = item & 31;
+  const uint8_t* src = in_tile + r * NQ_REC;
+  const uint32_t a8 = (r & 3) * 8;
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - (r & 3));
+  const uint32_t s0 = sw[0], s1 = sw[1], s2 = sw[2], s3 = sw[3], s4 = sw[4], s5 = sw[5];
+  // parent-aligned words: P[j] = parent bytes 4j .. 4j+3 (P5: byte 20 only)
+  uint32_t P[6] = {shf_r_wrap(s0, s1, a8), shf_r_wrap(s1, s2, a8), shf_r_wrap(s2, s3, a8),
+                   shf_r_wrap(s3, s4, a8), shf_r_wrap(s4, s5, a8), shf_r_wrap(s5, 0u, a8) & 0xFFu};
+  const uint32_t depth = P[0] & 0xFFu;
+  // child = parent with depth+1 and board[depth] <=> board[k]: XOR both bytes with their difference
+  const uint32_t p1 = 1u + depth, p2 = 1u + static_cast<uint32_t>(k);
+  const uint32_t D = static_cast<uint32_t>(src[p1]) ^ static_cast<uint32_t>(src[p2]);
+  const uint32_t x1 = D << ((p1 & 3u) * 8u), x2 = D << ((p2 & 3u) * 8u);
+  const uint32_t w1 = p1 >> 2, w2 = p2 >> 2;
+#pragma unroll
+  for (uint32_t j = 0; j < 6; j++) P[j] ^= (j == w1 ? x1 : 0u) ^ (j == w2 ? x2 : 0u);
+  P[0] += 1u;  // depth + 1 (depth < 255)
+  // realign to the image: the child occupies bytes b .. b+20 of six aligned words
+  const int b = B & 3;
+  const uint32_t b8 = b * 8;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(image + (B - b));
+  const uint32_t W0 = shf_l_wrap(0u, P[0], b8), W1 = shf_l_wrap(P[0], P[1], b8), W2 = shf_l_wrap(P[1], P[2], b8),
+                 W3 = shf_l_wrap(P[2], P[3], b8), W4 = shf_l_wrap(P[3], P[4], b8), W5 = shf_l_wrap(P[4], P[5], b8);
+  dw[1] = W1;
+  dw[2] = W2;
+  dw[3] = W3;
+  dw[4] = W4;
+  // first and last word are shared with the neighbouring children: only this child's bytes
+  uint8_t* d0 = reinterpret_cast<uint8_t*>(dw);
+  if (b == 0) {
+    dw[0] = W0;
+  } else {
+    if (b <= 1) d0[1] = static_cast<uint8_t>(W0 >> 8);
+    if (b <= 2) d0[2] = static_cast<uint8_t>(W0 >> 16);
+    d0[3] = static_cast<uint8_t>(W0 >> 24);
+  }
+  if (b == 3) {
+    dw[5] = W5;
+  } else {
+    d0[20] = static_cast<uint8_t>(W5);
+    if (b >= 1) d0[21] = static_cast<uint8_t>(W5 >> 8);
+    if (b >= 2) d0[22] = static_cast<uint8_t>(W5 >> 16);
+  }
+}
+
+// The same for a full warp of 32 consecutive children whose first one starts a word of the image (B = 4x for
+// lane 0, hence B & 3 == lane & 3): every word is stored whole — the word a child shares with its right-hand
+// neighbour is completed with the neighbour's first bytes by a warp shuffle, lane 31 ends on a word boundary
+// (32 * 21 bytes = 168 words).  `active` = the child exists; all 32 lanes must call.
+__device__ __forceinline__ void nq_build_child_warp(const uint8_t* in_tile, int item, uint8_t* image, int B,
+                                                    bool active) {
+  const int b = threadIdx.x & 3;
+  const uint32_t b8 = b * 8;
+  uint32_t W0 = 0, W1 = 0, W2 = 0, W3 = 0, W4 = 0, W5 = 0;
+  if (active) {
+    const int r = item >> 5, k = item & 31;
+    const uint8_t* src = in_tile + r * NQ_REC;
+    const uint32_t a8 = (r & 3) * 8;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - (r & 3));
+    const uint32_t s0 = sw[0], s1 = sw[1], s2 = sw[2], s3 = sw[3], s4 = sw[4], s5 = sw[5];
+    uint32_t P[6] = {shf_r_wrap(s0, s1, a8), shf_r_wrap(s1, s2, a8), shf_r_wrap(s2, s3, a8),
+                     shf_r_wrap(s3, s4, a8), shf_r_wrap(s4, s5, a8), shf_r_wrap(s5, 0u, a8) & 0xFFu};
+    const uint32_t depth = P[0] & 0xFFu;
+    const uint32_t p1 = 1u + depth, p2 = 1u + static_cast<uint32_t>(k);
+    const uint32_t D = static_cast<uint32_t>(src[p1]) ^ static_cast<uint32_t>(src[p2]);
+    const uint32_t x1 = D << ((p1 & 3u) * 8u), x2 = D << ((p2 & 3u) * 8u);
+    const uint32_t w1 = p1 >> 2, w2 = p2 >> 2;
+#pragma unroll
+    for (uint32_t j = 0; j < 6; j++) P[j] ^= (j == w1 ? x1 : 0u) ^ (j == w2 ? x2 : 0u);
+    P[0] += 1u;
+    W0 = shf_l_wrap(0u, P[0], b8);
+    W1 = shf_l_wrap(P[0], P[1], b8);
+    W2 = shf_l_wrap(P[1], P[2], b8);
+    W3 = shf_l_wrap(P[2], P[3], b8);
+    W4 = shf_l_wrap(P[3], P[4], b8);
+    W5 = shf_l_wrap(P[4], P[5], b8);
+  }
+  const uint32_t nb = __shfl_down_sync(0xFFFFFFFFu, W0, 1);  // the right-hand neighbour's first word (0 if none)
+  if (active) {
+    uint32_t* dw = reinterpret_cast<uint32_t*>(image + (B - b));
+    if (b == 0) dw[0] = W0;
+    dw[1] = W1;
+    dw[2] = W2;
+    dw[3] = W3;
+    dw[4] = W4;
+    dw[5] = b == 3 ? W5 : (W5 | nb);  // (a last child writes up to 3 zero bytes past the image's end)
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(NQ_THREADS) nq_expand_build_kernel(const uint8_t* __restrict__ arena,
+                                                                    const __grid_constant__ ExpandParams prm,
+                                                                    const uint32_t* __restrict__ cmask,
+                                                                    const int* __restrict__ tile_sums,
+                                                                    uint8_t* __restrict__ children,
+                                                                    ExpandState* __restrict__ st,
+                                                                    ExpandResult* __restrict__ res) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  NqBuildSmem& sm = *reinterpret_cast<NqBuildSmem*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  constexpr uint32_t IN_BYTES = NQ_TILE * NQ_REC;
+  const int first = blockIdx.x, stride = gridDim.x;
+  if (t == 0) {
+    mbar_init(&sm.full[0], 1);
+    mbar_init(&sm.full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  uint64_t pol = 0;
+  if (t == 0) pol = policy_evict_first();
+  auto issue = [&](int lin, int s) {  // thread 0: parents + masks of one tile
+    long long at, lo, hi;
+    piece_of(prm, lin, NQ_TILE, at, lo, hi);
+    const uint32_t nb = tile_load_bytes(at, hi, NQ_TILE, NQ_REC);
+    mbar_arrive_expect_tx(&sm.full[s], nb + NQ_TILE * 4);
+    bulk_g2s_stream(sm.in[s], arena + at * IN_BYTES, nb, &sm.full[s], pol);
+    bulk_g2s_stream(sm.mask[s], cmask + static_cast<long long>(lin) * NQ_TILE, NQ_TILE * 4, &sm.full[s], pol);
+  };
+  if (t == 0) {
+    if (first < prm.n_tiles) issue(first, 0);
+    if (first + stride < prm.n_tiles) issue(first + stride, 1);
+  }
+  expand_own_offsets<NQ_THREADS>(sm.scan, tile_sums, prm.n_tiles, first, stride);
+  expand_publish(sm.scan, st, res, prm.epoch, 0);
+  unsigned it = 0;
+  for (int lin = first; lin < prm.n_tiles; lin += stride, it++) {
+    const int s = it & 1;
+    mbar_wait(&sm.full[s], (it >> 1) & 1u);
+    const uint4 cmv = reinterpret_cast<const uint4*>(sm.mask[s])[t];
+    const uint32_t cm[4] = {cmv.x, cmv.y, cmv.z, cmv.w};
     const int mine = __popc(cm[0]) + __popc(cm[1]) + __popc(cm[2]) + __popc(cm[3]);
     int incl = mine;
 #pragma unroll
@@ -207,49 +308,46 @@ __global__ void __launch_bounds__(NQ_THREADS) nq_expand_write_kernel(const uint8
       if (lane >= o) incl += y;
     }
     if (lane == 31) sm.warp_tot[wid] = incl;
-    __syncthreads();
+    if (t == 0) bulk_wait_read<0>();  // the previous tile's bulk store has drained the staging image
+    __syncthreads();  // (A)
     int woff = 0, total = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       if (i < wid) woff += sm.warp_tot[i];
       total += sm.warp_tot[i];
     }
-    int pos = woff + incl - mine;  // index (within the tile) of this thread's first child
-    const long long g_byte0 = (static_cast<long long>(tile_off[tile])) * NQ_REC;  // byte offset in `children`
-    uint8_t* gdst = children + g_byte0;
-    const bool staged = total <= EXP_CAP;
-    // staging image starts at the same 16-byte phase as the global destination
-    uint8_t* sdst = sm.stage + (reinterpret_cast<uintptr_t>(gdst) & 15);
-    uint8_t* dst = staged ? sdst : gdst;
-    // ---- build the children: copy the parent's 21 bytes, then patch depth and the two swapped queens
+    const int pos0 = woff + incl - mine;  // index (within the tile) of this thread's first child
+    uint8_t* const gtile = children + static_cast<long long>(sm.scan.own[it]) * NQ_REC;
+    for (int c0 = 0; c0 < total; c0 += EXP_CAP) {  // windows of EXP_CAP children (one, except for dense tiles)
+      const int cnt = min(EXP_CAP, total - c0);
+      if (c0 > 0 && t == 0) bulk_wait_read<0>();  // the previous window's bulk store has drained the image
+      int pos = pos0 - c0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      uint32_t m = cm[q];
-      if (m) {
-        const uint8_t* src = sm.in + (4 * t + q) * NQ_REC;
-        uint8_t b[NQ_REC];
-#pragma unroll
-        for (int i = 0; i < NQ_REC; i++) b[i] = src[i];
-        const int depth = b[0];
-        const uint8_t qd = src[1 + depth];  // board[depth]
+      for (int q = 0; q < 4; q++) {
+        uint32_t m = cm[q];
         while (m) {
           const int k = __ffs(m) - 1;
           m &= m - 1;
-          uint8_t* c = dst + static_cast<long long>(pos) * NQ_REC;
-#pragma unroll
-          for (int i = 0; i < NQ_REC; i++) c[i] = b[i];
-          c[0] = static_cast<uint8_t>(depth + 1);
-          c[1 + depth] = src[1 + k];  // child.board[depth] <=> child.board[k]
-          c[1 + k] = qd;
+          if (pos >= 0 && pos < EXP_CAP) sm.item[pos] = static_cast<uint16_t>(((4 * t + q) << 5) | k);
           pos++;
         }
       }
-    }
-    if (staged) {
+      __syncthreads();  // (B) items
+      // one thread per child
+      uint8_t* gdst = gtile + static_cast<long long>(c0) * NQ_REC;
+      const int phase = static_cast<int>(reinterpret_cast<uintptr_t>(gdst) & 15);  // image and destination share it
+      uint8_t* sdst = sm.stage + phase;
+      // the first (-phase) & 3 children byte-wise, so that the warps' runs of 32 children start on a word
+      const int c_head = min(cnt, (4 - (phase & 3)) & 3);
+      if (t < c_head) nq_build_child(sm.in[s], sm.item[t], sm.stage, phase + t * NQ_REC);
+      for (int cb = c_head; cb < cnt; cb += NQ_THREADS) {
+        const int c = cb + t;
+        const bool active = c < cnt;
+        nq_build_child_warp(sm.in[s], active ? sm.item[c] : 0, sm.stage, phase + c * NQ_REC, active);
+      }
       fence_async_smem();
-      __syncthreads();
-      // head (< 16 B) and tail (< 16 B) by byte stores, the 16-byte aligned middle by one bulk store
-      const int bytes = total * NQ_REC;
+      __syncthreads();  // (C) image complete; item free
+      const int bytes = cnt * NQ_REC;
       const int head = min(bytes, static_cast<int>((16 - (reinterpret_cast<uintptr_t>(gdst) & 15)) & 15));
       const int mid = (bytes - head) & ~15;
       const int tail = bytes - head - mid;
@@ -258,10 +356,13 @@ __global__ void __launch_bounds__(NQ_THREADS) nq_expand_write_kernel(const uint8
       if (t == 0 && mid > 0) {
         bulk_s2g(gdst + head, sdst + head, static_cast<uint32_t>(mid));
         bulk_commit();
-        bulk_wait_read<0>();  // the staging image is rewritten by the next tile
       }
+      // the head / tail bytes are read from the image after (C) by threads 1..47, which reach the next (B)
+      // — after which the image is rewritten — only when they are done
     }
-    __syncthreads();
+    // in[s] and mask[s] are free: every thread passed (A) after reading its masks and, if the tile had
+    // children, (C) after reading the parents
+    if (t == 0 && lin + 2 * stride < prm.n_tiles) issue(lin + 2 * stride, s);
   }
   if (t == 0) bulk_wait_all();
 }

@@ -146,8 +146,48 @@ struct Base {
     if (d_out) cudaFree(d_out);
     if (h_in) cudaFreeHost(h_in);
     if (h_out) cudaFreeHost(h_out);
+    if (bounce) cudaFreeHost(bounce);
     if (stream) cudaStreamDestroy(stream);
     if (stream2) cudaStreamDestroy(stream2);
+  }
+
+  // Copies between a caller-owned host range and the device, on `stream`, synchronous.  A plain cudaMemcpy on
+  // a host range that only partly overlaps a range this handle page-locked earlier (a previous caller array
+  // at the same addresses) fails with "invalid argument", so: small copies bounce through a pinned buffer,
+  // large ones are page-locked first (which merges them with whatever they overlap).
+  uint8_t* bounce = nullptr;
+  static constexpr size_t kBounce = 1 << 20;
+  int copy_h2d(void* dst_d, const void* src_h, size_t bytes) {
+    if (!bytes) return TSB_OK;
+    if (bytes > kBounce && reg.ensure(src_h, bytes)) {
+      TSB_CUDA(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, stream));
+      TSB_CUDA(cudaStreamSynchronize(stream));
+      return TSB_OK;
+    }
+    if (!bounce) TSB_CUDA(cudaHostAlloc(&bounce, kBounce, cudaHostAllocPortable));
+    for (size_t off = 0; off < bytes; off += kBounce) {
+      const size_t n = std::min(kBounce, bytes - off);
+      std::memcpy(bounce, static_cast<const uint8_t*>(src_h) + off, n);
+      TSB_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst_d) + off, bounce, n, cudaMemcpyHostToDevice, stream));
+      TSB_CUDA(cudaStreamSynchronize(stream));
+    }
+    return TSB_OK;
+  }
+  int copy_d2h(void* dst_h, const void* src_d, size_t bytes) {
+    if (!bytes) return TSB_OK;
+    if (bytes > kBounce && reg.ensure(dst_h, bytes)) {
+      TSB_CUDA(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, stream));
+      TSB_CUDA(cudaStreamSynchronize(stream));
+      return TSB_OK;
+    }
+    if (!bounce) TSB_CUDA(cudaHostAlloc(&bounce, kBounce, cudaHostAllocPortable));
+    for (size_t off = 0; off < bytes; off += kBounce) {
+      const size_t n = std::min(kBounce, bytes - off);
+      TSB_CUDA(cudaMemcpyAsync(bounce, static_cast<const uint8_t*>(src_d) + off, n, cudaMemcpyDeviceToHost, stream));
+      TSB_CUDA(cudaStreamSynchronize(stream));
+      std::memcpy(static_cast<uint8_t*>(dst_h) + off, bounce, n);
+    }
+    return TSB_OK;
   }
 
   // Host-buffer evaluation shared by N-Queens and PFSP.  `launch(in_dev, out_dev, count, stream)`
@@ -228,23 +268,143 @@ int grid_for(K kernel, int threads, size_t smem, long long count, int tile, int 
 }  // namespace
 
 // ============================================================================ N-Queens
+struct PoolExtent {
+  long long b, e;  // arena positions [b, e)
+};
+
+// state of the fused expand kernels of one handle (expand_common.cuh)
+struct ExpandCtx {
+  uint32_t* d_cmask = nullptr;  // one child mask per parent of the round (tile-linear order)
+  int* d_tile = nullptr;        // per-tile child counts, then offsets
+  long long tile_cap = 0;       // tiles the two arrays above hold
+  int tile_records = 0;
+  tsb::ExpandState* d_st = nullptr;
+  tsb::ExpandResult* h_res = nullptr;  // pinned + mapped: written by the scan kernel of a round
+  tsb::ExpandResult* d_res = nullptr;  // device alias of h_res
+  unsigned epoch = 0;
+  int occ_count = 0, occ_build = 0;
+  bool attr_set = false;
+  // (clears are ordered on the stream the kernels run on: the handle's streams do not synchronise with the
+  // legacy default stream)
+  int reserve(long long tiles, int records_per_tile, cudaStream_t s, int best_init = 0x7FFFFFFF) {
+    if (!d_st) {
+      TSB_CUDA(cudaMalloc(&d_st, sizeof(tsb::ExpandState)));
+      const tsb::ExpandState init{0ull, best_init, 0};
+      TSB_CUDA(cudaMemcpyAsync(d_st, &init, sizeof(init), cudaMemcpyHostToDevice, s));
+      TSB_CUDA(cudaStreamSynchronize(s));  // `init` lives on this stack frame
+    }
+    if (!h_res) {
+      TSB_CUDA(cudaHostAlloc(&h_res, sizeof(tsb::ExpandResult), cudaHostAllocPortable | cudaHostAllocMapped));
+      TSB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_res), h_res, 0));
+    }
+    if (tiles > tile_cap || records_per_tile != tile_records) {
+      if (d_cmask) cudaFree(d_cmask);
+      if (d_tile) cudaFree(d_tile);
+      d_cmask = nullptr;
+      d_tile = nullptr;
+      tile_cap = 0;
+      const long long cap = std::max<long long>(tiles + tiles / 4 + 16, 1024);
+      TSB_CUDA(cudaMalloc(&d_cmask, static_cast<size_t>(cap) * records_per_tile * 4));
+      TSB_CUDA(cudaMalloc(&d_tile, static_cast<size_t>(cap) * sizeof(int)));
+      tile_cap = cap;
+      tile_records = records_per_tile;
+    }
+    return TSB_OK;
+  }
+  void release() {
+    if (d_cmask) cudaFree(d_cmask);
+    if (d_tile) cudaFree(d_tile);
+    if (d_st) cudaFree(d_st);
+    if (h_res) cudaFreeHost(h_res);
+    d_cmask = nullptr;
+    d_tile = nullptr;
+    d_st = nullptr;
+    h_res = d_res = nullptr;
+  }
+};
+
+// Device-resident pool: a stack of extents inside one arena of `rec`-byte nodes.  A round reads the newest
+// nodes in place (possibly spanning several extents) and appends the children above the top, so nothing is
+// copied; the holes left behind are reclaimed by compacting into the second arena when the top reaches the end.
+struct DevicePool {
+  uint8_t* arena[2] = {nullptr, nullptr};
+  long long cap = 0;  // nodes per arena
+  int cur = 0;
+  size_t rec = 0, slack = 0;
+  std::vector<PoolExtent> ext;
+  long long size = 0;
+  uint64_t compactions = 0;
+  long long top() const { return ext.empty() ? 0 : ext.back().e; }
+  size_t bytes(long long nodes) const { return static_cast<size_t>(nodes) * rec + slack + 64; }
+  int ensure_arena(int which, long long nodes) {
+    (void)nodes;
+    if (!arena[which]) TSB_CUDA(cudaMalloc(&arena[which], bytes(cap)));
+    return TSB_OK;
+  }
+  // all extents -> [0, size) of the other arena (or of fresh, larger arenas when `new_cap` > cap)
+  int compact(cudaStream_t s, long long new_cap) {
+    uint8_t* dst = nullptr;
+    const bool grow = new_cap > cap;
+    if (grow) {
+      TSB_CUDA(cudaMalloc(&dst, static_cast<size_t>(new_cap) * rec + slack + 64));
+    } else {
+      int rc = ensure_arena(cur ^ 1, cap);
+      if (rc != TSB_OK) return rc;
+      dst = arena[cur ^ 1];
+    }
+    long long at = 0;
+    for (const PoolExtent& x : ext) {
+      TSB_CUDA(cudaMemcpyAsync(dst + at * rec, arena[cur] + x.b * rec, static_cast<size_t>(x.e - x.b) * rec,
+                               cudaMemcpyDeviceToDevice, s));
+      at += x.e - x.b;
+    }
+    TSB_CUDA(cudaStreamSynchronize(s));
+    if (grow) {
+      if (arena[0]) cudaFree(arena[0]);
+      if (arena[1]) cudaFree(arena[1]);
+      arena[0] = dst;
+      arena[1] = nullptr;
+      cur = 0;
+      cap = new_cap;
+    } else {
+      cur ^= 1;
+    }
+    ext.clear();
+    if (at) ext.push_back({0, at});
+    ++compactions;
+    return TSB_OK;
+  }
+  // room for `extra` nodes above the top
+  int reserve(cudaStream_t s, long long extra, long long min_cap) {
+    if (cap == 0) {
+      cap = std::max<long long>(min_cap, extra + 1024);
+      int rc = ensure_arena(cur, cap);
+      if (rc != TSB_OK) return rc;
+    }
+    if (top() + extra <= cap) return TSB_OK;
+    const long long need = size + extra;
+    return compact(s, need > cap ? std::max<long long>(2 * cap, need + need / 2) : cap);
+  }
+  void release() {
+    if (arena[0]) cudaFree(arena[0]);
+    if (arena[1]) cudaFree(arena[1]);
+    arena[0] = arena[1] = nullptr;
+    ext.clear();
+    size = 0;
+    cap = 0;
+  }
+};
+
 struct tsb_nq : Base {
   int N = 0, g = 1;
   int variant = 0;  // env TSB200_NQ_VARIANT (kernel A/B experiments)
   int occ = 0;      // cached CTAs per SM
   bool attr_set = false;
   // fused expand (evaluate + generate_children on the device) and the device-resident pool
-  uint8_t* d_cmask = nullptr;
-  int* d_tile = nullptr;
-  long long exp_cap = 0;  // parents the two arrays above are sized for
-  tsb::ExpandCounters* d_ctr = nullptr;
-  tsb::ExpandCounters* h_ctr = nullptr;  // pinned
-  uint8_t* d_children = nullptr;         // host-buffer expand: device image of the children
+  ExpandCtx ex;
+  uint8_t* d_children = nullptr;  // host-buffer expand: device image of the children
   size_t d_children_bytes = 0;
-  bool exp_attr_set = false;
-  int occ_count = 0, occ_write = 0;
-  uint8_t* pool = nullptr;  // device-resident pool: `pool_size` nodes of 21 B, capacity `pool_cap`
-  long long pool_size = 0, pool_cap = 0;
+  DevicePool pool;
 };
 
 namespace {
@@ -285,63 +445,73 @@ int launch_nq(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaS
 
 namespace {
 
-int nq_expand_reserve(tsb_nq* h, long long count) {
-  if (count > h->exp_cap) {
-    if (h->d_cmask) cudaFree(h->d_cmask);
-    if (h->d_tile) cudaFree(h->d_tile);
-    h->d_cmask = nullptr;
-    h->d_tile = nullptr;
-    h->exp_cap = 0;
-    const long long cap = std::max<long long>(count, h->M_max);
-    TSB_CUDA(cudaMalloc(&h->d_cmask, static_cast<size_t>(cap + tsb::NQ_TILE) * 4));
-    TSB_CUDA(cudaMalloc(&h->d_tile, static_cast<size_t>(cap / tsb::NQ_TILE + 4) * sizeof(int)));
-    h->exp_cap = cap;
+// tile table of a round: pieces in logical order -> ExpandParams
+int make_params(const std::vector<PoolExtent>& pieces, int tile_records, tsb::ExpandParams* prm) {
+  if (pieces.empty() || pieces.size() > tsb::EXP_MAX_PIECES) return TSB_EINVAL;
+  std::memset(prm, 0, sizeof(*prm));
+  long long cum = 0;
+  for (size_t i = 0; i < pieces.size(); i++) {
+    const PoolExtent& x = pieces[i];
+    const long long t0 = x.b / tile_records, t1 = (x.e + tile_records - 1) / tile_records;
+    prm->piece[i].lo = x.b;
+    prm->piece[i].hi = x.e;
+    prm->piece[i].first_tile = t0;
+    prm->piece[i].tile_cum = static_cast<int>(cum);
+    cum += t1 - t0;
   }
-  if (!h->d_ctr) TSB_CUDA(cudaMalloc(&h->d_ctr, sizeof(tsb::ExpandCounters)));
-  if (!h->h_ctr) TSB_CUDA(cudaHostAlloc(&h->h_ctr, sizeof(tsb::ExpandCounters), cudaHostAllocPortable));
+  if (cum > INT_MAX / 2) return TSB_EINVAL;
+  prm->n_pieces = static_cast<int>(pieces.size());
+  prm->n_tiles = static_cast<int>(cum);
   return TSB_OK;
 }
 
-// K1 + K2 + K3 on `s`; children_d may have any alignment; synchronous (the counts come back)
+// one evaluate + generate_children round over `pieces` of `arena` (count, build); children packed at
+// `children_d`.  Synchronous: the counts come back through the host-mapped result record.
 template <int N>
-int nq_expand_n(tsb_nq* h, const uint8_t* parents_d, long long count, uint8_t* children_d, cudaStream_t s,
-                unsigned long long* n_children, unsigned long long* n_solutions) {
-  int rc = nq_expand_reserve(h, count);
+int nq_expand_n(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& pieces, uint8_t* children_d,
+                cudaStream_t s, unsigned long long* n_children, unsigned long long* n_solutions) {
+  tsb::ExpandParams prm;
+  int rc = make_params(pieces, tsb::NQ_TILE, &prm);
+  if (rc != TSB_OK) return rc;
+  ExpandCtx& ex = h->ex;
+  rc = ex.reserve(prm.n_tiles, tsb::NQ_TILE, s);
   if (rc != TSB_OK) return rc;
   auto k1 = tsb::nq_expand_count_kernel<N>;
-  auto k3 = tsb::nq_expand_write_kernel<N>;
-  const size_t smem1 = sizeof(tsb::NqCountSmem<N>) + 128, smem3 = sizeof(tsb::NqWriteSmem) + 128;
-  if (!h->exp_attr_set) {
+  auto k3 = tsb::nq_expand_build_kernel<N>;
+  const size_t smem1 = sizeof(tsb::NqCountSmem) + 128, smem3 = sizeof(tsb::NqBuildSmem) + 128;
+  if (!ex.attr_set) {
     TSB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
     TSB_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem3)));
-    h->exp_attr_set = true;
+    ex.attr_set = true;
   }
-  const long long tiles = (count + tsb::NQ_TILE - 1) / tsb::NQ_TILE;
+  const long long recs = static_cast<long long>(prm.n_tiles) * tsb::NQ_TILE;
   int g1 = 1, g3 = 1;
-  rc = grid_for(k1, tsb::NQ_THREADS, smem1, count, tsb::NQ_TILE, h->di.sms, &g1, &h->occ_count);
+  rc = grid_for(k1, tsb::NQ_THREADS, smem1, recs, tsb::NQ_TILE, h->di.sms, &g1, &ex.occ_count);
   if (rc != TSB_OK) return rc;
-  rc = grid_for(k3, tsb::NQ_THREADS, smem3, tiles * tsb::NQ_TILE, tsb::NQ_TILE, h->di.sms, &g3, &h->occ_write);
+  rc = grid_for(k3, tsb::NQ_THREADS, smem3, recs, tsb::NQ_TILE, h->di.sms, &g3, &ex.occ_build);
   if (rc != TSB_OK) return rc;
-  TSB_CUDA(cudaMemsetAsync(h->d_ctr, 0, sizeof(tsb::ExpandCounters), s));
-  k1<<<g1, tsb::NQ_THREADS, smem1, s>>>(parents_d, h->d_cmask, count, h->d_tile, h->d_ctr);
-  tsb::scan_tiles_kernel<<<1, 1024, 0, s>>>(h->d_tile, static_cast<int>(tiles), h->d_ctr);
-  k3<<<g3, tsb::NQ_THREADS, smem3, s>>>(parents_d, reinterpret_cast<const uint32_t*>(h->d_cmask), h->d_tile, count,
-                                        children_d);
+  prm.epoch = ++ex.epoch;
+  if ((prm.n_tiles + g3 - 1) / g3 > tsb::EXP_MAX_OWN) return TSB_EINVAL;  // (M_max * N < 2^31 keeps this far away)
+  k1<<<g1, tsb::NQ_THREADS, smem1, s>>>(arena, prm, ex.d_cmask, ex.d_tile, ex.d_st);
+  k3<<<g3, tsb::NQ_THREADS, smem3, s>>>(arena, prm, ex.d_cmask, ex.d_tile, children_d, ex.d_st, ex.d_res);
   TSB_CUDA(cudaGetLastError());
-  h->launches += 3;
-  TSB_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(tsb::ExpandCounters), cudaMemcpyDeviceToHost, s));
+  h->launches += 2;
   TSB_CUDA(cudaStreamSynchronize(s));
-  *n_children = h->h_ctr->children;
-  *n_solutions = h->h_ctr->solutions;
+  if (ex.h_res->epoch != prm.epoch) {
+    g_last_cuda_error = "expand kernels did not publish their result";
+    return TSB_ECUDA;
+  }
+  *n_children = ex.h_res->children;
+  *n_solutions = ex.h_res->solutions;
   return TSB_OK;
 }
 
-int nq_expand_dispatch(tsb_nq* h, const uint8_t* parents_d, long long count, uint8_t* children_d, cudaStream_t s,
-                       unsigned long long* nc, unsigned long long* ns) {
+int nq_expand_dispatch(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& pieces, uint8_t* children_d,
+                       cudaStream_t s, unsigned long long* nc, unsigned long long* ns) {
   switch (h->N) {
 #define TSB_NQ_CASE(n) \
   case n:              \
-    return nq_expand_n<n>(h, parents_d, count, children_d, s, nc, ns);
+    return nq_expand_n<n>(h, arena, pieces, children_d, s, nc, ns);
     TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
     TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
     TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
@@ -349,6 +519,29 @@ int nq_expand_dispatch(tsb_nq* h, const uint8_t* parents_d, long long count, uin
 #undef TSB_NQ_CASE
   }
   return TSB_EINVAL;
+}
+
+// the newest n nodes of a pool, as pieces in logical order
+void pool_top_pieces(const DevicePool& p, long long n, std::vector<PoolExtent>* pieces) {
+  pieces->clear();
+  long long left = n;
+  for (size_t i = p.ext.size(); i-- > 0 && left > 0;) {
+    const long long t = std::min(left, p.ext[i].e - p.ext[i].b);
+    pieces->insert(pieces->begin(), PoolExtent{p.ext[i].e - t, p.ext[i].e});
+    left -= t;
+  }
+}
+// drop the newest n nodes
+void pool_pop(DevicePool& p, long long n) {
+  long long left = n;
+  while (left > 0 && !p.ext.empty()) {
+    PoolExtent& x = p.ext.back();
+    const long long t = std::min(left, x.e - x.b);
+    x.e -= t;
+    left -= t;
+    if (x.e == x.b) p.ext.pop_back();
+  }
+  p.size -= n;
 }
 
 }  // namespace
@@ -477,12 +670,9 @@ void tsb_nq_destroy(tsb_nq* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->d_cmask) cudaFree(h->d_cmask);
-  if (h->d_tile) cudaFree(h->d_tile);
-  if (h->d_ctr) cudaFree(h->d_ctr);
-  if (h->h_ctr) cudaFreeHost(h->h_ctr);
+  h->ex.release();
   if (h->d_children) cudaFree(h->d_children);
-  if (h->pool) cudaFree(h->pool);
+  h->pool.release();
   h->fini();
   delete h;
 }
@@ -497,7 +687,8 @@ int tsb_nq_expand_device(tsb_nq* h, const void* parents_d, int count, void* chil
   if (reinterpret_cast<uintptr_t>(parents_d) & 15) return TSB_EALIGN;
   TSB_CUDA(cudaSetDevice(h->device));
   unsigned long long nc = 0, ns = 0;
-  int rc = nq_expand_dispatch(h, static_cast<const uint8_t*>(parents_d), count, static_cast<uint8_t*>(children_d),
+  const std::vector<PoolExtent> pieces{{0, count}};
+  int rc = nq_expand_dispatch(h, static_cast<const uint8_t*>(parents_d), pieces, static_cast<uint8_t*>(children_d),
                               stream ? static_cast<cudaStream_t>(stream) : h->stream, &nc, &ns);
   *n_children = nc;
   *n_solutions = ns;
@@ -519,78 +710,85 @@ int tsb_nq_expand(tsb_nq* h, const void* parents, int count, void* children, uin
     TSB_CUDA(cudaMalloc(&h->d_children, need));
     h->d_children_bytes = need;
   }
-  const size_t in_b = sizeof(tsb_nq_node) * static_cast<size_t>(count);
-  const bool in_locked = h->reg.ensure(parents, in_b);
-  const void* src = parents;
-  if (!in_locked) {
-    int rc = h->ensure_staging();
-    if (rc != TSB_OK) return rc;
-    std::memcpy(h->h_in, parents, in_b);
-    src = h->h_in;
-  }
-  TSB_CUDA(cudaMemcpyAsync(h->d_in, src, in_b, cudaMemcpyHostToDevice, h->stream));
+  int rc = h->copy_h2d(h->d_in, parents, sizeof(tsb_nq_node) * static_cast<size_t>(count));
+  if (rc != TSB_OK) return rc;
   unsigned long long nc = 0, ns = 0;
-  int rc = nq_expand_dispatch(h, h->d_in, count, h->d_children, h->stream, &nc, &ns);
+  const std::vector<PoolExtent> pieces{{0, count}};
+  rc = nq_expand_dispatch(h, h->d_in, pieces, h->d_children, h->stream, &nc, &ns);
   if (rc != TSB_OK) return rc;
   *n_children = nc;
   *n_solutions = ns;
   if (nc > capacity) return TSB_ENOMEM;  // the caller's children array is too small; counts are valid
-  if (nc) TSB_CUDA(cudaMemcpy(children, h->d_children, nc * sizeof(tsb_nq_node), cudaMemcpyDeviceToHost));
-  return TSB_OK;
+  return h->copy_d2h(children, h->d_children, nc * sizeof(tsb_nq_node));
 }
+
+namespace {
+// arena capacity a handle starts with: four worst-case rounds (every slot of every parent survives)
+// (env TSB200_POOL_CAP overrides, so that tests can force compaction and growth)
+long long env_pool_cap() {
+  const char* v = std::getenv("TSB200_POOL_CAP");
+  return v ? std::atoll(v) : 0;
+}
+long long nq_pool_min_cap(const tsb_nq* h) {
+  if (const long long c = env_pool_cap(); c > 0) return c;
+  return std::max<long long>(1LL << 22, 4LL * h->M_max * h->N);
+}
+void nq_pool_setup(tsb_nq* h) {
+  h->pool.rec = sizeof(tsb_nq_node);
+  h->pool.slack = static_cast<size_t>(tsb::NQ_TILE) * sizeof(tsb_nq_node);  // full-tile loads may run past the top
+}
+}  // namespace
 
 int tsb_nq_pool_push(tsb_nq* h, const void* nodes, int64_t n) {
   if (!h || n < 0 || (n && !nodes)) return TSB_EINVAL;
   TSB_CUDA(cudaSetDevice(h->device));
-  const long long need = h->pool_size + n;
-  if (need > h->pool_cap) {
-    // room for two worst-case rounds up front, so that growth (a device-wide realloc + copy) stays rare
-    const long long cap = std::max<long long>({need, 2 * h->pool_cap, 1LL << 20, 2LL * h->M_max * h->N});
-    uint8_t* np = nullptr;
-    TSB_CUDA(cudaMalloc(&np, static_cast<size_t>(cap) * sizeof(tsb_nq_node) + 64));
-    if (h->pool_size)
-      TSB_CUDA(cudaMemcpy(np, h->pool, static_cast<size_t>(h->pool_size) * sizeof(tsb_nq_node), cudaMemcpyDeviceToDevice));
-    if (h->pool) cudaFree(h->pool);
-    h->pool = np;
-    h->pool_cap = cap;
-  }
-  if (n)
-    TSB_CUDA(cudaMemcpy(h->pool + h->pool_size * sizeof(tsb_nq_node), nodes, static_cast<size_t>(n) * sizeof(tsb_nq_node),
-                        cudaMemcpyHostToDevice));
-  h->pool_size = need;
+  nq_pool_setup(h);
+  int rc = h->pool.reserve(h->stream, n, nq_pool_min_cap(h));
+  if (rc != TSB_OK) return rc;
+  if (n == 0) return TSB_OK;
+  const long long at = h->pool.top();
+  // (on the handle's non-blocking stream, which the kernels of the next round are ordered after)
+  rc = h->copy_h2d(h->pool.arena[h->pool.cur] + at * sizeof(tsb_nq_node), nodes,
+                   static_cast<size_t>(n) * sizeof(tsb_nq_node));
+  if (rc != TSB_OK) return rc;
+  if (h->pool.ext.empty())
+    h->pool.ext.push_back({at, at + n});
+  else
+    h->pool.ext.back().e += n;
+  h->pool.size += n;
   return TSB_OK;
 }
 
-int64_t tsb_nq_pool_size(const tsb_nq* h) { return h ? h->pool_size : -1; }
+int64_t tsb_nq_pool_size(const tsb_nq* h) { return h ? h->pool.size : -1; }
 
 int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_children, uint64_t* n_solutions) {
   if (!h || m < 1 || M < 1 || M > h->M_max || !n_parents || !n_children || !n_solutions) return TSB_EINVAL;
   *n_parents = 0;
   *n_children = *n_solutions = 0;
-  if (h->pool_size < m) return TSB_OK;  // popBackBulk returns 0 below m (lib/commons/Pool.chpl:50-59)
+  DevicePool& p = h->pool;
+  if (p.size < m) return TSB_OK;  // popBackBulk returns 0 below m (lib/commons/Pool.chpl:50-59)
   TSB_CUDA(cudaSetDevice(h->device));
-  const long long n = std::min<long long>(h->pool_size, M);
-  const long long base = h->pool_size - n;
-  // room for the worst case (every slot of every parent survives) before anything is overwritten
+  const long long n = std::min<long long>(p.size, M);
+  // room above the top for the worst case (every slot of every parent survives); the chunk itself is read
+  // in place, as the newest pieces of the extent stack
+  std::vector<PoolExtent> pieces;
+  pool_top_pieces(p, n, &pieces);
   int rc = TSB_OK;
-  const long long worst = base + n * h->N;
-  if (worst > h->pool_cap) {
-    const long long keep = h->pool_size;
-    const long long cap = std::max<long long>(worst, 2 * h->pool_cap);
-    uint8_t* np = nullptr;
-    TSB_CUDA(cudaMalloc(&np, static_cast<size_t>(cap) * sizeof(tsb_nq_node) + 64));
-    TSB_CUDA(cudaMemcpy(np, h->pool, static_cast<size_t>(keep) * sizeof(tsb_nq_node), cudaMemcpyDeviceToDevice));
-    cudaFree(h->pool);
-    h->pool = np;
-    h->pool_cap = cap;
-  }
-  // the newest n nodes become the chunk (order preserved); their children are appended where they were
-  TSB_CUDA(cudaMemcpyAsync(h->d_in, h->pool + base * sizeof(tsb_nq_node), static_cast<size_t>(n) * sizeof(tsb_nq_node),
-                           cudaMemcpyDeviceToDevice, h->stream));
-  unsigned long long nc = 0, ns = 0;
-  rc = nq_expand_dispatch(h, h->d_in, n, h->pool + base * sizeof(tsb_nq_node), h->stream, &nc, &ns);
+  if (pieces.size() > tsb::EXP_MAX_PIECES)
+    rc = p.compact(h->stream, p.cap);
+  if (rc == TSB_OK) rc = p.reserve(h->stream, n * h->N, nq_pool_min_cap(h));
   if (rc != TSB_OK) return rc;
-  h->pool_size = base + static_cast<long long>(nc);
+  pool_top_pieces(p, n, &pieces);  // (positions change when the pool was compacted)
+  const long long top = p.top();
+  unsigned long long nc = 0, ns = 0;
+  uint8_t* arena = p.arena[p.cur];
+  rc = nq_expand_dispatch(h, arena, pieces, arena + top * sizeof(tsb_nq_node), h->stream, &nc, &ns);
+  if (rc != TSB_OK) return rc;
+  pool_pop(p, n);
+  if (nc) {
+    p.ext.push_back({top, top + static_cast<long long>(nc)});
+    p.size += static_cast<long long>(nc);
+  }
   *n_parents = n;
   *n_children = nc;
   *n_solutions = ns;
@@ -599,12 +797,20 @@ int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_ch
 
 int tsb_nq_pool_drain(tsb_nq* h, void* nodes, int64_t capacity, int64_t* n) {
   if (!h || !n || capacity < 0) return TSB_EINVAL;
-  *n = h->pool_size;
-  if (h->pool_size > capacity) return TSB_ENOMEM;
+  DevicePool& p = h->pool;
+  *n = p.size;
+  if (p.size > capacity) return TSB_ENOMEM;
   TSB_CUDA(cudaSetDevice(h->device));
-  if (h->pool_size)
-    TSB_CUDA(cudaMemcpy(nodes, h->pool, static_cast<size_t>(h->pool_size) * sizeof(tsb_nq_node), cudaMemcpyDeviceToHost));
-  h->pool_size = 0;
+  long long at = 0;
+  for (const PoolExtent& x : p.ext) {  // extents are the pool in logical (oldest first) order
+    int rc = h->copy_d2h(static_cast<uint8_t*>(nodes) + at * sizeof(tsb_nq_node),
+                         p.arena[p.cur] + x.b * sizeof(tsb_nq_node),
+                         static_cast<size_t>(x.e - x.b) * sizeof(tsb_nq_node));
+    if (rc != TSB_OK) return rc;
+    at += x.e - x.b;
+  }
+  p.ext.clear();
+  p.size = 0;
   return TSB_OK;
 }
 
@@ -689,8 +895,9 @@ int tsb_pfsp_create(tsb_pfsp** out, int device, int jobs, int machines, int M_ma
   auto upload = [&]() -> int {
     TSB_CUDA(cudaMalloc(&h->d_tab1, sizeof(t1)));
     TSB_CUDA(cudaMalloc(&h->d_tab2, sizeof(t2)));
-    TSB_CUDA(cudaMemcpy(h->d_tab1, &t1, sizeof(t1), cudaMemcpyHostToDevice));
-    TSB_CUDA(cudaMemcpy(h->d_tab2, &t2, sizeof(t2), cudaMemcpyHostToDevice));
+    TSB_CUDA(cudaMemcpyAsync(h->d_tab1, &t1, sizeof(t1), cudaMemcpyHostToDevice, h->stream));
+    TSB_CUDA(cudaMemcpyAsync(h->d_tab2, &t2, sizeof(t2), cudaMemcpyHostToDevice, h->stream));
+    TSB_CUDA(cudaStreamSynchronize(h->stream));
     return TSB_OK;
   };
   if (rc == TSB_OK) rc = upload();

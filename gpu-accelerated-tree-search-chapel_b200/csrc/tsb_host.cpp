@@ -156,6 +156,36 @@ void nq_gpu_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool
   tsb_nq_destroy(h);
 }
 
+// the same loop with the task's pool resident on the device (tsb_nq_pool_*): popBackBulk, evaluate and
+// generate_children of a round are one kernel; the host reads three counters per round
+void nq_devpool_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResult& r) {
+  tsb_nq* h = nullptr;
+  r.rc = tsb_nq_create(&h, device, N, g, M);
+  if (r.rc != TSB_OK) return;
+  r.rc = tsb_nq_pool_push(h, &pool.el[pool.front], static_cast<int64_t>(pool.size));
+  pool.front = 0;
+  pool.size = 0;
+  while (r.rc == TSB_OK) {
+    int64_t np = 0;
+    uint64_t nc = 0, ns = 0;
+    r.rc = tsb_nq_pool_step(h, m, M, &np, &nc, &ns);
+    if (r.rc != TSB_OK || np == 0) break;
+    r.tree += nc;
+    r.sol += ns;
+    ++r.offloads;
+    r.parents += static_cast<uint64_t>(np);
+  }
+  if (r.rc == TSB_OK) {  // fewer than m nodes left: back to the host pool for step 3
+    const int64_t left = tsb_nq_pool_size(h);
+    std::vector<tsb_nq_node> rest(static_cast<size_t>(left) + 1);
+    int64_t n = 0;
+    r.rc = tsb_nq_pool_drain(h, rest.data(), left, &n);
+    for (int64_t i = 0; i < n && r.rc == TSB_OK; i++) pool.pushBack(rest[i]);
+  }
+  r.launches = tsb_nq_kernel_launches(h);
+  tsb_nq_destroy(h);
+}
+
 // static strided split of the warm-up pool (nqueens_multigpu_chpl.chpl:199-226)
 template <class Node>
 void static_split(Pool<Node>& pool, int D, std::vector<Pool<Node>>& multi) {
@@ -462,10 +492,10 @@ int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out) {
   return TSB_OK;
 }
 
-int tsb_nq_search_device(int N, int g, int m, int M, tsb_search_stats* out) {
-  if (!out || N < 1 || N > TSB_MAX_QUEENS || g < 1 || m < 1 || M < 1) return TSB_EINVAL;
+int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* out) {
+  if (!out || N < 1 || N > TSB_MAX_QUEENS || g < 1 || m < 1 || M < 1 || D < 1 || D > 8) return TSB_EINVAL;
   std::memset(out, 0, sizeof(*out));
-  if (int rc = tsb_init_devices(1); rc != TSB_OK) return rc;
+  if (int rc = tsb_init_devices(D); rc != TSB_OK) return rc;
   Pool<tsb_nq_node> pool;
   tsb_nq_node root{};
   for (int i = 0; i < N; i++) root.board[i] = static_cast<uint8_t>(i);
@@ -473,39 +503,36 @@ int tsb_nq_search_device(int N, int g, int m, int M, tsb_search_stats* out) {
   uint64_t tree = 0, sol = 0;
   tsb_nq_node parent;
   double t0 = now_s();
-  while (pool.size < static_cast<size_t>(m)) {  // step 1 on the CPU, as in the reference
+  while (pool.size < static_cast<size_t>(D) * m) {  // step 1 on the CPU, as in the reference
     if (!pool.popFront(parent)) break;
     nq_decompose(N, parent, tree, sol, pool);
   }
   double t1 = now_s();
   out->t_step1 = t1 - t0;
-  tsb_nq* h = nullptr;  // step 2: the pool moves to the device and stays there
-  int rc = tsb_nq_create(&h, 0, N, g, M);
-  if (rc != TSB_OK) return rc;
-  rc = tsb_nq_pool_push(h, &pool.el[pool.front], static_cast<int64_t>(pool.size));
-  pool.front = 0;
-  pool.size = 0;
-  while (rc == TSB_OK) {
-    int64_t np = 0;
-    uint64_t nc = 0, ns = 0;
-    rc = tsb_nq_pool_step(h, m, M, &np, &nc, &ns);
-    if (rc != TSB_OK || np == 0) break;
-    tree += nc;
-    sol += ns;
-    out->offloads += 1;
-    out->offloaded_parents += static_cast<uint64_t>(np);
+  // step 2: every task's pool moves to its device and stays there (same static split as tsb_nq_search)
+  std::vector<GpuTaskResult> res(D);
+  const int ndev = std::max(1, tsb_device_count());
+  if (D == 1) {
+    nq_devpool_task(0, N, g, m, M, pool, res[0]);
+  } else {
+    std::vector<Pool<tsb_nq_node>> multi;
+    static_split(pool, D, multi);
+    std::vector<std::thread> th;
+    for (int gid = 0; gid < D; gid++)
+      th.emplace_back([&, gid] { nq_devpool_task(gid % ndev, N, g, m, M, multi[gid], res[gid]); });
+    for (auto& x : th) x.join();
+    for (int gid = 0; gid < D; gid++)
+      while (multi[gid].popBack(parent)) pool.pushBack(parent);
   }
-  if (rc == TSB_OK) {  // fewer than m nodes left: back to the host pool for step 3
-    const int64_t left = tsb_nq_pool_size(h);
-    std::vector<tsb_nq_node> rest(static_cast<size_t>(left) + 1);
-    int64_t n = 0;
-    rc = tsb_nq_pool_drain(h, rest.data(), left, &n);
-    for (int64_t i = 0; i < n && rc == TSB_OK; i++) pool.pushBack(rest[i]);
+  for (int gid = 0; gid < D; gid++) {
+    if (res[gid].rc != TSB_OK) return res[gid].rc;
+    tree += res[gid].tree;
+    sol += res[gid].sol;
+    out->offloads += res[gid].offloads;
+    out->offloaded_parents += res[gid].parents;
+    out->kernel_launches += res[gid].launches;
+    out->per_gpu_tree[gid] = res[gid].tree;
   }
-  out->kernel_launches = tsb_nq_kernel_launches(h);
-  tsb_nq_destroy(h);
-  if (rc != TSB_OK) return rc;
-  out->per_gpu_tree[0] = tree;
   double t2 = now_s();
   out->t_step2 = t2 - t1;
   while (pool.popBack(parent)) nq_decompose(N, parent, tree, sol, pool);  // step 3

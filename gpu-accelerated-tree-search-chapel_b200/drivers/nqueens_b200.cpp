@@ -35,7 +35,7 @@ int main(int argc, char** argv) {
               "Resolution of the %d-Queens instance\n  with %d safety check(s) per evaluation\n"
               "=================================================\n", D > 1 ? "Multi-GPU" : "Single-GPU", N, g);
   tsb_search_stats st;
-  const int rc = devpool ? tsb_nq_search_device(N, g, m, M, &st) : tsb_nq_search(N, g, m, M, D, &st);
+  const int rc = devpool ? tsb_nq_search_device(N, g, m, M, D, &st) : tsb_nq_search(N, g, m, M, D, &st);
   if (rc != TSB_OK) {
     std::fprintf(stderr, "tsb_nq_search: %s (%s)\n", tsb_strerror(rc), tsb_last_cuda_error());
     return 3;

@@ -81,7 +81,7 @@ SYMBOLS = {
     "tsb_pfsp_tables_build": (_i, [C.POINTER(PfspTables), _i]),
     "tsb_pfsp_create_from_tables": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(PfspTables)]),
     "tsb_nq_search": (_i, [_i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
-    "tsb_nq_search_device": (_i, [_i, _i, _i, _i, C.POINTER(SearchStats)]),
+    "tsb_nq_search_device": (_i, [_i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
     "tsb_pfsp_search": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
 }
 

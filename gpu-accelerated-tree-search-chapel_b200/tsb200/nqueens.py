@@ -108,8 +108,8 @@ def nqueens_search(N: int = 14, g: int = 1, m: int = 25, M: int = 50000, D: int 
     return st
 
 
-def nqueens_search_device(N: int = 14, g: int = 1, m: int = 25, M: int = 50000) -> SearchStats:
-    """same 3-step search, the pool of step 2 resident on the device (tsb_nq_pool_*)"""
+def nqueens_search_device(N: int = 14, g: int = 1, m: int = 25, M: int = 50000, D: int = 1) -> SearchStats:
+    """same 3-step search, the pool(s) of step 2 resident on the device(s) (tsb_nq_pool_*)"""
     st = SearchStats()
-    check(lib().tsb_nq_search_device(N, g, m, M, C.byref(st)), "tsb_nq_search_device")
+    check(lib().tsb_nq_search_device(N, g, m, M, D, C.byref(st)), "tsb_nq_search_device")
     return st

@@ -113,8 +113,10 @@ int tsb_nq_expand_device(tsb_nq* h, const void* parents_d /*16-B aligned*/, int 
 
 /* ---- device-resident pool: the reference's SinglePool (lib/commons/Pool.chpl) kept in
  * HBM.  push = pushBack of host nodes; step = one offload round of nqueens_gpu_chpl.chpl:197-215 done
- * entirely on the device: popBackBulk(m, M) (nothing below m, else the newest min(size, M) nodes, order
- * preserved), evaluate, generate_children appended to the pool; drain = move what is left to the host. */
+ * entirely on the device by ONE kernel: popBackBulk(m, M) (nothing below m, else the newest min(size, M)
+ * nodes, order preserved, read in place), evaluate, generate_children appended to the pool; drain = move what
+ * is left to the host (logical order).  The pool's logical content after every round is byte-identical to
+ * the reference's host pool. */
 int tsb_nq_pool_push(tsb_nq* h, const void* nodes, int64_t n);
 int64_t tsb_nq_pool_size(const tsb_nq* h);
 int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_children, uint64_t* n_solutions);
@@ -185,9 +187,10 @@ typedef struct {
 
 /* nqueens_gpu_chpl.chpl:152-248 / nqueens_multigpu_chpl.chpl:158-352 */
 int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out);
-/* the same 3-step search with the pool of step 2 resident on the device (tsb_nq_pool_*): identical chunk
- * sequence, identical counts; the host only reads three counters per round.  D = 1. */
-int tsb_nq_search_device(int N, int g, int m, int M, tsb_search_stats* out);
+/* the same 3-step search with the pool(s) of step 2 resident on the device(s) (tsb_nq_pool_*): identical
+ * chunk sequence, identical counts; the host only reads three counters per round.  D > 1 = the same static
+ * strided split, one device pool per GPU. */
+int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* out);
 /* pfsp_gpu_chpl.chpl:306-431 / pfsp_multigpu_chpl.chpl:316-560 */
 int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out);
 

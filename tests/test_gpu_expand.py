@@ -72,12 +72,24 @@ def test_device_pool_is_byte_identical_to_the_reference_pool():
     del host
 
 
-@pytest.mark.parametrize("N,m,M", [(10, 25, 50000), (12, 25, 50000), (12, 5, 300), (13, 25, 4096), (14, 25, 50000),
-                                   (15, 25, 1 << 20)])
-def test_device_resident_search_counts(golden_dir, N, m, M):
+def test_device_pool_compaction_and_growth(golden_dir, monkeypatch):
+    """a tiny arena (TSB200_POOL_CAP) forces the extent stack to be compacted into the second arena and the
+    arenas to grow many times during a search; counts and chunk sequence must not change"""
+    monkeypatch.setenv("TSB200_POOL_CAP", "3000")
+    N, m, M = 12, 25, 500
     counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
     st = tsb200.nqueens_search_device(N, 1, m, M)
+    ref = po.nq_search_offload(N, 1, m, M, 1)
     assert (st.explored_tree, st.explored_sol) == (counts["tree"], counts["sol"])
-    ref = po.nq_search_offload(N, 1, m, M, 1)  # same chunk sequence as the reference driver
     assert (st.offloads, st.offloaded_parents) == (ref.offloads, ref.offloaded_parents)
-    assert st.kernel_launches == 3 * st.offloads
+
+
+@pytest.mark.parametrize("N,m,M,D", [(10, 25, 50000, 1), (12, 25, 50000, 1), (12, 5, 300, 1), (13, 25, 4096, 1),
+                                     (14, 25, 50000, 1), (15, 25, 1 << 20, 1), (13, 25, 2000, 3), (14, 25, 50000, 4)])
+def test_device_resident_search_counts(golden_dir, N, m, M, D):
+    counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
+    st = tsb200.nqueens_search_device(N, 1, m, M, D)
+    assert (st.explored_tree, st.explored_sol) == (counts["tree"], counts["sol"])
+    ref = po.nq_search_offload(N, 1, m, M, D)  # same chunk sequence as the reference driver
+    assert (st.offloads, st.offloaded_parents) == (ref.offloads, ref.offloaded_parents)
+    assert st.kernel_launches == 2 * st.offloads  # count, build
