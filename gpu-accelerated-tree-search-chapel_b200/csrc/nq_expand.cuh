@@ -24,7 +24,10 @@
 
 namespace tsb {
 
-constexpr int EXP_CAP = 1024;  // children per pass of the shared staging image (a tile averages ~512; denser tiles take several passes)
+#ifndef TSB_EXP_CAP
+#define TSB_EXP_CAP 1024
+#endif
+constexpr int EXP_CAP = TSB_EXP_CAP;  // children per pass of the shared staging image (a tile averages ~512; denser tiles take several passes)
 
 template <int N, int Q>
 __device__ __forceinline__ uint32_t nq_child_mask(NqParent<N, Q, 0>& p) {

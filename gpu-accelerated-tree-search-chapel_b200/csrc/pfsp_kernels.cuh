@@ -76,12 +76,12 @@ struct Lb1Smem {
 // with it in the children loop, so a warp whose 32 parents have (nearly) the same depth executes
 // close to the average number of steps instead of max-prefix + max-children of a mixed warp.
 __device__ __forceinline__ int depth_sorted_parent(int32_t* bin, uint8_t* order, const uint8_t* in_tile,
-                                                   int records) {
+                                                   int rec_lo, int rec_hi) {
   const int t = threadIdx.x;
   if (t < 32) bin[t] = 0;
   __syncthreads();
-  int d = 31;  // threads beyond the tile's records sort last and stay idle
-  if (t < records) {
+  int d = 31;  // records outside [rec_lo, rec_hi) sort last and stay idle
+  if (t >= rec_lo && t < rec_hi) {
     d = reinterpret_cast<const int32_t*>(in_tile)[22 * t + 1] + 1;  // limit1 + 1 in 0..20
     d = min(max(d, 0), 30);
   }
@@ -183,17 +183,20 @@ __device__ __forceinline__ int child_bound(const int (&F)[M], const int (&R)[M],
   }
 }
 
-template <int KIND, int M>
-__device__ __forceinline__ void lb1_compute_tile(Lb1Smem& sm, const uint8_t* in_tile, uint8_t* out_tile,
-                                                 int records) {
+// Bounds of all children of the tile's parents [rec_lo, rec_hi).  `emit(t, limit1, g, v)` receives, for parent
+// t and every group g of four slots with at least one live slot (k = 4g..4g+3 > limit1), the four bounds.
+// Returns the record this thread was given by the depth sort (a permutation of the tile's 128 records).
+template <int KIND, int M, typename Emit>
+__device__ __forceinline__ int lb1_compute_tile(Lb1Smem& sm, const uint8_t* in_tile, int rec_lo, int rec_hi,
+                                                Emit&& emit) {
   const PfspLb1Tables& tab = sm.tab;
-  const int t = depth_sorted_parent(sm.bin, sm.order, in_tile, records);
-  if (t >= records) return;
+  const int t = depth_sorted_parent(sm.bin, sm.order, in_tile, rec_lo, rec_hi);
+  if (t < rec_lo || t >= rec_hi) return t;
   // the node: 22 ints as 11 8-byte loads
   const int2* node2 = reinterpret_cast<const int2*>(in_tile) + 11 * t;
   int prmu[PF_MAXJ];
   const int2 head = node2[0];
-  const int limit1 = head.y;
+  const int limit1 = min(max(head.y, -1), PF_MAXJ - 1);
 #pragma unroll
   for (int q = 0; q < 10; q++) {
     const int2 v = node2[1 + q];
@@ -239,10 +242,9 @@ __device__ __forceinline__ void lb1_compute_tile(Lb1Smem& sm, const uint8_t* in_
 #pragma unroll
     for (int j = 0; j < M; j++) R[j] += B[j];
   }
-  int4* out4 = reinterpret_cast<int4*>(out_tile) + 5 * t;
-  // children in groups of four slots = one 16-byte store.  A group with at least one live slot
-  // evaluates all four slots without branches (four independent recurrences to interleave); the
-  // values of slots k <= limit1 are unspecified by contract.
+  // children in groups of four slots.  A group with at least one live slot evaluates all four slots without
+  // branches (four independent recurrences to interleave); the values of slots k <= limit1 are unspecified
+  // by contract.
 #pragma unroll
   for (int g = 0; g < 5; g++) {
     if (4 * g + 3 > limit1) {
@@ -253,9 +255,10 @@ __device__ __forceinline__ void lb1_compute_tile(Lb1Smem& sm, const uint8_t* in_
         load_row<M>(tab, prmu[4 * g + c], row);
         v[c] = child_bound<KIND, M>(F, R, B, row);
       }
-      out4[g] = make_int4(v[0], v[1], v[2], v[3]);
+      emit(t, limit1, g, v);
     }
   }
+  return t;
 }
 
 template <int KIND, int M>
@@ -267,7 +270,10 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_lb1_kernel(const uint8_t* __r
   stage_blob(&sm.tab, tables, sizeof(PfspLb1Tables), &sm.tab_bar);
   run_tile_pipeline<LB1_STAGES, PF_TILE, PF_REC, PF_MAXJ * 4>(
       sm.tiles, parents, bounds, count, [&sm](const uint8_t* in_tile, uint8_t* out_tile, int n, long long) {
-        lb1_compute_tile<KIND, M>(sm, in_tile, out_tile, n);
+        // one 16-byte store per group of four slots (stride 80 B = odd multiple of 16 B: conflict free)
+        lb1_compute_tile<KIND, M>(sm, in_tile, 0, n, [out_tile](int t, int, int g, const int (&v)[4]) {
+          reinterpret_cast<int4*>(out_tile)[5 * t + g] = make_int4(v[0], v[1], v[2], v[3]);
+        });
       });
 }
 
@@ -295,22 +301,23 @@ struct Lb2Smem {
   int32_t n_items;
 };
 
-template <int M>
-__device__ __forceinline__ void lb2_compute_tile(Lb2Smem& sm, const uint8_t* in_tile, uint8_t* out_tile,
-                                                 int records, int best) {
+// `emit(p, k, lb)` receives the bound of every live (parent p, slot k) of the tile's parents [rec_lo, rec_hi);
+// `dead(p, k)` is called for the slots below the live range (the evaluator zeroes them).
+template <int M, typename Emit, typename Dead>
+__device__ __forceinline__ void lb2_compute_tile(Lb2Smem& sm, const uint8_t* in_tile, int rec_lo, int rec_hi,
+                                                 int best, Emit&& emit, Dead&& dead) {
   const int t = threadIdx.x;
   const PfspLb1Tables& tab = sm.tab1;
   const PfspLb2Tables& t2 = sm.tab2;
   const int jobs = tab.jobs;
   const int32_t* nodes = reinterpret_cast<const int32_t*>(in_tile);
-  int32_t* out = reinterpret_cast<int32_t*>(out_tile);
 
   if (t == 0) sm.n_items = 0;
   __syncthreads();
   // ---- phase A
-  if (t < records) {
+  if (t >= rec_lo && t < rec_hi) {
     const int32_t* node = nodes + 22 * t;
-    const int limit1 = node[1];
+    const int limit1 = min(max(node[1], -1), PF_MAXJ - 1);
     int F[M], R[M];
     parent_front_remain<M>(tab, node, limit1, false, F, R);  // lb2 children always have limit1 >= 0
 #pragma unroll
@@ -324,7 +331,7 @@ __device__ __forceinline__ void lb2_compute_tile(Lb2Smem& sm, const uint8_t* in_
       if (k > limit1)
         sm.items[base++] = static_cast<uint16_t>((t << 5) | k);
       else
-        out[jobs * t + k] = 0;
+        dead(t, k);
     }
   }
   __syncthreads();
@@ -367,7 +374,7 @@ __device__ __forceinline__ void lb2_compute_tile(Lb2Smem& sm, const uint8_t* in_
       lb = max(lb, tmp1);
       if (lb > best) break;
     }
-    out[jobs * p + k] = lb;
+    emit(p, k, lb);
   }
 }
 
@@ -389,7 +396,11 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_lb2_kernel(const uint8_t* __r
   mbar_wait(&sm.tab_bar[0], 0);
   run_tile_pipeline<LB2_STAGES, PF_TILE, PF_REC, PF_MAXJ * 4>(
       sm.tiles, parents, bounds, count, [&sm, best](const uint8_t* in_tile, uint8_t* out_tile, int n, long long) {
-        lb2_compute_tile<M>(sm, in_tile, out_tile, n, best);
+        int32_t* out = reinterpret_cast<int32_t*>(out_tile);
+        const int jobs = sm.tab1.jobs;
+        lb2_compute_tile<M>(
+            sm, in_tile, 0, n, best, [out, jobs](int p, int k, int lb) { out[jobs * p + k] = lb; },
+            [out, jobs](int p, int k) { out[jobs * p + k] = 0; });
       });
 }
 

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "nq_expand.cuh"
+#include "pfsp_expand.cuh"
 #include "nq_kernel.cuh"
 #include "pfsp_kernels.cuh"
 #include "tsb200.h"
@@ -31,6 +32,11 @@ thread_local std::string g_last_cuda_error;
     }                                                                                          \
   } while (0)
 
+// (env TSB200_POOL_CAP overrides the initial arena capacity, so that tests can force compaction and growth)
+long long env_pool_cap() {
+  const char* v = std::getenv("TSB200_POOL_CAP");
+  return v ? std::atoll(v) : 0;
+}
 int env_xfer() {
   const char* s = std::getenv("TSB200_XFER");
   if (!s) return TSB_XFER_AUTO;
@@ -553,6 +559,16 @@ struct tsb_pfsp : Base {
   tsb::PfspLb2Tables* d_tab2 = nullptr;
   bool attr_set[3] = {false, false, false};
   int occ[3] = {0, 0, 0};
+  // fused expand + device-resident pool
+  ExpandCtx ex;
+  bool ex_attr[4] = {false, false, false, false};  // count lb1_d, lb1, lb2; build
+  int ex_occ[4] = {0, 0, 0, 0};
+  uint8_t* d_children = nullptr;
+  size_t d_children_bytes = 0;
+  DevicePool pool;
+  uint64_t slow_rounds = 0;
+  std::vector<tsb_pfsp_node> h_chunk, h_kids;  // slow path scratch
+  std::vector<int32_t> h_bounds;
 };
 
 namespace {
@@ -603,6 +619,159 @@ int launch_pfsp(tsb_pfsp* h, int lb_kind, const uint8_t* in, uint8_t* out, long 
   if (h->mt == 10) { TSB_PF_DISPATCH(10) }
   TSB_PF_DISPATCH(20)
 #undef TSB_PF_DISPATCH
+}
+
+}  // namespace
+
+namespace {
+
+inline int clamp_best(int64_t best64) {
+  return best64 > INT_MAX ? INT_MAX : best64 < INT_MIN ? INT_MIN : static_cast<int>(best64);
+}
+
+template <int M>
+int pfsp_expand_m(tsb_pfsp* h, int lb_kind, const uint8_t* arena, const tsb::ExpandParams& prm, uint8_t* children_d,
+                  cudaStream_t s) {
+  ExpandCtx& ex = h->ex;
+  const long long recs = static_cast<long long>(prm.n_tiles) * tsb::PF_TILE;
+  auto k3 = tsb::pfsp_expand_build_kernel;
+  const size_t smem3 = sizeof(tsb::PfBuildSmem) + 128;
+  if (!h->ex_attr[3]) {
+    TSB_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem3)));
+    h->ex_attr[3] = true;
+  }
+  int g1 = 1, g3 = 1;
+  int rc = grid_for(k3, tsb::PF_THREADS, smem3, recs, tsb::PF_TILE, h->di.sms, &g3, &h->ex_occ[3]);
+  if (rc != TSB_OK) return rc;
+  if ((prm.n_tiles + g3 - 1) / g3 > tsb::EXP_MAX_OWN) return TSB_EINVAL;
+  if (lb_kind == TSB_LB2) {
+    auto k1 = tsb::pfsp_expand_count_lb2_kernel<M>;
+    const size_t smem1 = sizeof(tsb::Lb2CountSmem) + 128;
+    if (!h->ex_attr[2]) {
+      TSB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
+      h->ex_attr[2] = true;
+    }
+    rc = grid_for(k1, tsb::PF_THREADS, smem1, recs, tsb::PF_TILE, h->di.sms, &g1, &h->ex_occ[2]);
+    if (rc != TSB_OK) return rc;
+    k1<<<g1, tsb::PF_THREADS, smem1, s>>>(arena, prm, h->d_tab1, h->d_tab2, ex.d_cmask, ex.d_tile, ex.d_st);
+  } else if (lb_kind == TSB_LB1) {
+    auto k1 = tsb::pfsp_expand_count_lb1_kernel<1, M>;
+    const size_t smem1 = sizeof(tsb::Lb1CountSmem) + 128;
+    if (!h->ex_attr[1]) {
+      TSB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
+      h->ex_attr[1] = true;
+    }
+    rc = grid_for(k1, tsb::PF_THREADS, smem1, recs, tsb::PF_TILE, h->di.sms, &g1, &h->ex_occ[1]);
+    if (rc != TSB_OK) return rc;
+    k1<<<g1, tsb::PF_THREADS, smem1, s>>>(arena, prm, h->d_tab1, ex.d_cmask, ex.d_tile, ex.d_st);
+  } else {
+    auto k1 = tsb::pfsp_expand_count_lb1_kernel<0, M>;
+    const size_t smem1 = sizeof(tsb::Lb1CountSmem) + 128;
+    if (!h->ex_attr[0]) {
+      TSB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
+      h->ex_attr[0] = true;
+    }
+    rc = grid_for(k1, tsb::PF_THREADS, smem1, recs, tsb::PF_TILE, h->di.sms, &g1, &h->ex_occ[0]);
+    if (rc != TSB_OK) return rc;
+    k1<<<g1, tsb::PF_THREADS, smem1, s>>>(arena, prm, h->d_tab1, ex.d_cmask, ex.d_tile, ex.d_st);
+  }
+  k3<<<g3, tsb::PF_THREADS, smem3, s>>>(arena, prm, ex.d_cmask, ex.d_tile, children_d, ex.d_st, ex.d_res);
+  TSB_CUDA(cudaGetLastError());
+  h->launches += 2;
+  return TSB_OK;
+}
+
+// generate_children of pfsp_gpu_chpl.chpl:273-303 on host arrays (the sequential rule, used by the slow path)
+void pfsp_generate_children_host(int jobs, const tsb_pfsp_node* parents, int size, const int32_t* bounds,
+                                 int64_t* best, std::vector<tsb_pfsp_node>* kids, uint64_t* sol) {
+  for (int i = 0; i < size; i++) {
+    const tsb_pfsp_node& parent = parents[i];
+    const int depth = parent.depth;
+    for (int j = parent.limit1 + 1; j < jobs; j++) {
+      const int32_t lb = bounds[j + static_cast<size_t>(i) * jobs];
+      if (depth + 1 == jobs) {
+        ++*sol;
+        if (lb < *best) *best = lb;
+      } else if (lb < *best) {
+        tsb_pfsp_node c = parent;
+        c.depth = depth + 1;
+        c.limit1 = parent.limit1 + 1;
+        std::swap(c.prmu[depth], c.prmu[j]);
+        kids->push_back(c);
+      }
+    }
+  }
+}
+
+// One evaluate + generate_children round over `pieces` of `arena`; children packed at `children_d` (room for
+// n * jobs nodes).  *best is read and updated with the reference's semantics.  Synchronous.
+int pfsp_expand_round(tsb_pfsp* h, int lb_kind, const uint8_t* arena, const std::vector<PoolExtent>& pieces,
+                      uint8_t* children_d, cudaStream_t s, int64_t* best, unsigned long long* n_children,
+                      unsigned long long* n_solutions) {
+  tsb::ExpandParams prm;
+  int rc = make_params(pieces, tsb::PF_TILE, &prm);
+  if (rc != TSB_OK) return rc;
+  const int best_launch = clamp_best(*best);
+  ExpandCtx& ex = h->ex;
+  rc = ex.reserve(prm.n_tiles, tsb::PF_TILE, s);
+  if (rc != TSB_OK) return rc;
+  prm.epoch = ++ex.epoch;
+  prm.best = best_launch;
+  if (h->mt == 5)
+    rc = pfsp_expand_m<5>(h, lb_kind, arena, prm, children_d, s);
+  else if (h->mt == 10)
+    rc = pfsp_expand_m<10>(h, lb_kind, arena, prm, children_d, s);
+  else
+    rc = pfsp_expand_m<20>(h, lb_kind, arena, prm, children_d, s);
+  if (rc != TSB_OK) return rc;
+  TSB_CUDA(cudaStreamSynchronize(s));
+  if (ex.h_res->epoch != prm.epoch) {
+    g_last_cuda_error = "expand kernels did not publish their result";
+    return TSB_ECUDA;
+  }
+  if (ex.h_res->best >= best_launch) {  // no leaf of the chunk improved best: the launch-value masks are exact
+    *n_children = ex.h_res->children;
+    *n_solutions = ex.h_res->solutions;
+    return TSB_OK;
+  }
+  // ---- slow path: a leaf lowered best inside this chunk, which changes what the rest of the chunk pushes
+  // (sequential rule).  Redo the round: bounds through the evaluator, children on the host.
+  ++h->slow_rounds;
+  long long n = 0;
+  for (const PoolExtent& x : pieces) n += x.e - x.b;
+  if (n > h->M_max) return TSB_EINVAL;
+  long long at = 0;
+  if (!(arena == h->d_in && pieces.size() == 1 && pieces[0].b == 0))
+    for (const PoolExtent& x : pieces) {  // the chunk, contiguous
+      TSB_CUDA(cudaMemcpyAsync(h->d_in + at * sizeof(tsb_pfsp_node), arena + x.b * sizeof(tsb_pfsp_node),
+                               static_cast<size_t>(x.e - x.b) * sizeof(tsb_pfsp_node), cudaMemcpyDeviceToDevice, s));
+      at += x.e - x.b;
+    }
+  rc = launch_pfsp(h, lb_kind, h->d_in, h->d_out, n, *best, s);
+  if (rc != TSB_OK) return rc;
+  h->h_chunk.resize(static_cast<size_t>(n));
+  h->h_bounds.resize(static_cast<size_t>(n) * h->jobs);
+  rc = h->copy_d2h(h->h_chunk.data(), h->d_in, static_cast<size_t>(n) * sizeof(tsb_pfsp_node));
+  if (rc == TSB_OK) rc = h->copy_d2h(h->h_bounds.data(), h->d_out, static_cast<size_t>(n) * h->jobs * 4);
+  if (rc != TSB_OK) return rc;
+  h->h_kids.clear();
+  uint64_t sol = 0;
+  pfsp_generate_children_host(h->jobs, h->h_chunk.data(), static_cast<int>(n), h->h_bounds.data(), best, &h->h_kids,
+                              &sol);
+  rc = h->copy_h2d(children_d, h->h_kids.data(), h->h_kids.size() * sizeof(tsb_pfsp_node));
+  if (rc != TSB_OK) return rc;
+  *n_children = h->h_kids.size();
+  *n_solutions = sol;
+  return TSB_OK;
+}
+
+long long pfsp_pool_min_cap(const tsb_pfsp* h) {
+  if (const long long c = env_pool_cap(); c > 0) return c;
+  return std::max<long long>(1LL << 20, 4LL * h->M_max * h->jobs);
+}
+void pfsp_pool_setup(tsb_pfsp* h) {
+  h->pool.rec = sizeof(tsb_pfsp_node);
+  h->pool.slack = static_cast<size_t>(tsb::PF_TILE) * sizeof(tsb_pfsp_node);
 }
 
 }  // namespace
@@ -724,11 +893,6 @@ int tsb_nq_expand(tsb_nq* h, const void* parents, int count, void* children, uin
 
 namespace {
 // arena capacity a handle starts with: four worst-case rounds (every slot of every parent survives)
-// (env TSB200_POOL_CAP overrides, so that tests can force compaction and growth)
-long long env_pool_cap() {
-  const char* v = std::getenv("TSB200_POOL_CAP");
-  return v ? std::atoll(v) : 0;
-}
 long long nq_pool_min_cap(const tsb_nq* h) {
   if (const long long c = env_pool_cap(); c > 0) return c;
   return std::max<long long>(1LL << 22, 4LL * h->M_max * h->N);
@@ -915,6 +1079,9 @@ void tsb_pfsp_destroy(tsb_pfsp* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->d_tab1) cudaFree(h->d_tab1);
   if (h->d_tab2) cudaFree(h->d_tab2);
+  h->ex.release();
+  if (h->d_children) cudaFree(h->d_children);
+  h->pool.release();
   h->fini();
   delete h;
 }
@@ -950,5 +1117,130 @@ int tsb_pfsp_set_xfer(tsb_pfsp* h, int mode) {
   return TSB_OK;
 }
 uint64_t tsb_pfsp_kernel_launches(const tsb_pfsp* h) { return h ? h->launches : 0; }
+
+uint64_t tsb_pfsp_slow_rounds(const tsb_pfsp* h) { return h ? h->slow_rounds : 0; }
+
+int tsb_pfsp_expand_device(tsb_pfsp* h, int lb_kind, const void* parents_d, int count, int64_t* best,
+                           void* children_d, uint64_t* n_children, uint64_t* n_solutions, void* stream) {
+  if (!h || count < 0 || lb_kind < 0 || lb_kind > 2 || !best || !n_children || !n_solutions) return TSB_EINVAL;
+  if (lb_kind == TSB_LB2 && h->pairs == 0) return TSB_EINVAL;
+  *n_children = *n_solutions = 0;
+  if (count == 0) return TSB_OK;
+  if (!parents_d || !children_d || count > h->M_max) return TSB_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(parents_d) & 15) || (reinterpret_cast<uintptr_t>(children_d) & 7)) return TSB_EALIGN;
+  TSB_CUDA(cudaSetDevice(h->device));
+  unsigned long long nc = 0, ns = 0;
+  const std::vector<PoolExtent> pieces{{0, count}};
+  int rc = pfsp_expand_round(h, lb_kind, static_cast<const uint8_t*>(parents_d), pieces,
+                             static_cast<uint8_t*>(children_d), stream ? static_cast<cudaStream_t>(stream) : h->stream,
+                             best, &nc, &ns);
+  *n_children = nc;
+  *n_solutions = ns;
+  return rc;
+}
+
+int tsb_pfsp_expand(tsb_pfsp* h, int lb_kind, const void* parents, int count, int64_t* best, void* children,
+                    uint64_t capacity, uint64_t* n_children, uint64_t* n_solutions) {
+  if (!h || count < 0 || count > h->M_max || lb_kind < 0 || lb_kind > 2 || !best || !n_children || !n_solutions)
+    return TSB_EINVAL;
+  if (lb_kind == TSB_LB2 && h->pairs == 0) return TSB_EINVAL;
+  *n_children = *n_solutions = 0;
+  if (count == 0) return TSB_OK;
+  if (!parents || !children) return TSB_EINVAL;
+  TSB_CUDA(cudaSetDevice(h->device));
+  const size_t need = static_cast<size_t>(h->M_max) * h->jobs * sizeof(tsb_pfsp_node) + 64;
+  if (h->d_children_bytes < need) {
+    if (h->d_children) cudaFree(h->d_children);
+    h->d_children = nullptr;
+    h->d_children_bytes = 0;
+    TSB_CUDA(cudaMalloc(&h->d_children, need));
+    h->d_children_bytes = need;
+  }
+  int rc = h->copy_h2d(h->d_in, parents, sizeof(tsb_pfsp_node) * static_cast<size_t>(count));
+  if (rc != TSB_OK) return rc;
+  unsigned long long nc = 0, ns = 0;
+  const std::vector<PoolExtent> pieces{{0, count}};
+  rc = pfsp_expand_round(h, lb_kind, h->d_in, pieces, h->d_children, h->stream, best, &nc, &ns);
+  if (rc != TSB_OK) return rc;
+  *n_children = nc;
+  *n_solutions = ns;
+  if (nc > capacity) return TSB_ENOMEM;
+  return h->copy_d2h(children, h->d_children, nc * sizeof(tsb_pfsp_node));
+}
+
+int tsb_pfsp_pool_push(tsb_pfsp* h, const void* nodes, int64_t n) {
+  if (!h || n < 0 || (n && !nodes)) return TSB_EINVAL;
+  TSB_CUDA(cudaSetDevice(h->device));
+  pfsp_pool_setup(h);
+  int rc = h->pool.reserve(h->stream, n, pfsp_pool_min_cap(h));
+  if (rc != TSB_OK) return rc;
+  if (n == 0) return TSB_OK;
+  const long long at = h->pool.top();
+  rc = h->copy_h2d(h->pool.arena[h->pool.cur] + at * sizeof(tsb_pfsp_node), nodes,
+                   static_cast<size_t>(n) * sizeof(tsb_pfsp_node));
+  if (rc != TSB_OK) return rc;
+  if (h->pool.ext.empty())
+    h->pool.ext.push_back({at, at + n});
+  else
+    h->pool.ext.back().e += n;
+  h->pool.size += n;
+  return TSB_OK;
+}
+
+int64_t tsb_pfsp_pool_size(const tsb_pfsp* h) { return h ? h->pool.size : -1; }
+
+int tsb_pfsp_pool_step(tsb_pfsp* h, int lb_kind, int m, int M, int64_t* best, int64_t* n_parents,
+                       uint64_t* n_children, uint64_t* n_solutions) {
+  if (!h || lb_kind < 0 || lb_kind > 2 || m < 1 || M < 1 || M > h->M_max || !best || !n_parents || !n_children ||
+      !n_solutions)
+    return TSB_EINVAL;
+  if (lb_kind == TSB_LB2 && h->pairs == 0) return TSB_EINVAL;
+  *n_parents = 0;
+  *n_children = *n_solutions = 0;
+  DevicePool& p = h->pool;
+  if (p.size < m) return TSB_OK;  // popBackBulk returns 0 below m (lib/commons/Pool.chpl:50-59)
+  TSB_CUDA(cudaSetDevice(h->device));
+  const long long n = std::min<long long>(p.size, M);
+  std::vector<PoolExtent> pieces;
+  pool_top_pieces(p, n, &pieces);
+  int rc = TSB_OK;
+  if (pieces.size() > tsb::EXP_MAX_PIECES) rc = p.compact(h->stream, p.cap);
+  if (rc == TSB_OK) rc = p.reserve(h->stream, n * h->jobs + 2, pfsp_pool_min_cap(h));
+  if (rc != TSB_OK) return rc;
+  pool_top_pieces(p, n, &pieces);
+  const long long top = (p.top() + 1) & ~1LL;  // children start on a 16-byte boundary (88 B records)
+  unsigned long long nc = 0, ns = 0;
+  uint8_t* arena = p.arena[p.cur];
+  rc = pfsp_expand_round(h, lb_kind, arena, pieces, arena + top * sizeof(tsb_pfsp_node), h->stream, best, &nc, &ns);
+  if (rc != TSB_OK) return rc;
+  pool_pop(p, n);
+  if (nc) {
+    p.ext.push_back({top, top + static_cast<long long>(nc)});
+    p.size += static_cast<long long>(nc);
+  }
+  *n_parents = n;
+  *n_children = nc;
+  *n_solutions = ns;
+  return TSB_OK;
+}
+
+int tsb_pfsp_pool_drain(tsb_pfsp* h, void* nodes, int64_t capacity, int64_t* n) {
+  if (!h || !n || capacity < 0) return TSB_EINVAL;
+  DevicePool& p = h->pool;
+  *n = p.size;
+  if (p.size > capacity) return TSB_ENOMEM;
+  TSB_CUDA(cudaSetDevice(h->device));
+  long long at = 0;
+  for (const PoolExtent& x : p.ext) {
+    int rc = h->copy_d2h(static_cast<uint8_t*>(nodes) + at * sizeof(tsb_pfsp_node),
+                         p.arena[p.cur] + x.b * sizeof(tsb_pfsp_node),
+                         static_cast<size_t>(x.e - x.b) * sizeof(tsb_pfsp_node));
+    if (rc != TSB_OK) return rc;
+    at += x.e - x.b;
+  }
+  p.ext.clear();
+  p.size = 0;
+  return TSB_OK;
+}
 
 }  // extern "C"

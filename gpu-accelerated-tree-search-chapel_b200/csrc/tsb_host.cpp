@@ -357,6 +357,36 @@ void pfsp_gpu_task(int device, const tsb_pfsp_tables& t, int lb_kind, int m, int
   tsb_pfsp_destroy(h);
 }
 
+// the same loop with the task's pool resident on the device (tsb_pfsp_pool_*)
+void pfsp_devpool_task(int device, const tsb_pfsp_tables& t, int lb_kind, int m, int M, Pool<tsb_pfsp_node>& pool,
+                       GpuTaskResult& r) {
+  tsb_pfsp* h = nullptr;
+  r.rc = tsb_pfsp_create_from_tables(&h, device, M, &t);
+  if (r.rc != TSB_OK) return;
+  r.rc = tsb_pfsp_pool_push(h, &pool.el[pool.front], static_cast<int64_t>(pool.size));
+  pool.front = 0;
+  pool.size = 0;
+  while (r.rc == TSB_OK) {
+    int64_t np = 0;
+    uint64_t nc = 0, ns = 0;
+    r.rc = tsb_pfsp_pool_step(h, lb_kind, m, M, &r.best, &np, &nc, &ns);
+    if (r.rc != TSB_OK || np == 0) break;
+    r.tree += nc;
+    r.sol += ns;
+    ++r.offloads;
+    r.parents += static_cast<uint64_t>(np);
+  }
+  if (r.rc == TSB_OK) {
+    const int64_t left = tsb_pfsp_pool_size(h);
+    std::vector<tsb_pfsp_node> rest(static_cast<size_t>(left) + 1);
+    int64_t n = 0;
+    r.rc = tsb_pfsp_pool_drain(h, rest.data(), left, &n);
+    for (int64_t i = 0; i < n && r.rc == TSB_OK; i++) pool.pushBack(rest[i]);
+  }
+  r.launches = tsb_pfsp_kernel_launches(h);
+  tsb_pfsp_destroy(h);
+}
+
 }  // namespace
 
 // ====================================================================== exported
@@ -542,7 +572,7 @@ int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* ou
   return TSB_OK;
 }
 
-int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out) {
+static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, bool devpool, tsb_search_stats* out) {
   if (!out || lb_kind < 0 || lb_kind > 2 || (ub != 0 && ub != 1) || m < 1 || M < 1 || D < 1 || D > 8)
     return TSB_EINVAL;
   std::memset(out, 0, sizeof(*out));
@@ -570,14 +600,15 @@ int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_sear
   std::vector<GpuTaskResult> res(D);
   const int ndev = std::max(1, tsb_device_count());
   for (auto& r : res) r.best = best;  // per-task best_l = best (pfsp_multigpu_chpl.chpl:384)
+  auto task = devpool ? pfsp_devpool_task : pfsp_gpu_task;
   if (D == 1) {
-    pfsp_gpu_task(0, t, lb_kind, m, M, pool, res[0]);
+    task(0, t, lb_kind, m, M, pool, res[0]);
   } else {
     std::vector<Pool<tsb_pfsp_node>> multi;
     static_split(pool, D, multi);
     std::vector<std::thread> th;
     for (int gid = 0; gid < D; gid++)
-      th.emplace_back([&, gid] { pfsp_gpu_task(gid % ndev, t, lb_kind, m, M, multi[gid], res[gid]); });
+      th.emplace_back([&, gid] { task(gid % ndev, t, lb_kind, m, M, multi[gid], res[gid]); });
     for (auto& x : th) x.join();
     for (int gid = 0; gid < D; gid++)
       while (multi[gid].popBack(parent)) pool.pushBack(parent);
@@ -600,6 +631,13 @@ int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_sear
   out->explored_sol = sol;
   out->best = best;
   return TSB_OK;
+}
+
+int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out) {
+  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, false, out);
+}
+int tsb_pfsp_search_device(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out) {
+  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, true, out);
 }
 
 }  // extern "C"

@@ -8,7 +8,7 @@
 #include "tsb200.h"
 
 int main(int argc, char** argv) {
-  int inst = 14, ub = 1, m = 25, M = 50000, D = 1, lb = TSB_LB1;
+  int inst = 14, ub = 1, m = 25, M = 50000, D = 1, lb = TSB_LB1, devpool = 0;
   const char* lbs = "lb1";
   for (int i = 1; i < argc; i++) {
     if (!std::strcmp(argv[i], "-h") || !std::strcmp(argv[i], "--help")) {
@@ -26,7 +26,8 @@ int main(int argc, char** argv) {
     }
     int* dst = !std::strcmp(argv[i], "--inst") ? &inst : !std::strcmp(argv[i], "--ub") ? &ub
              : !std::strcmp(argv[i], "--m") ? &m : !std::strcmp(argv[i], "--M") ? &M
-             : !std::strcmp(argv[i], "--D") ? &D : nullptr;
+             : !std::strcmp(argv[i], "--D") ? &D
+             : !std::strcmp(argv[i], "--devpool") ? &devpool : nullptr;  // 1: pool(s) of step 2 resident on the GPU
     if (dst) *dst = std::atoi(argv[++i]);
   }
   if (m <= 0 || M <= 0) { std::fprintf(stderr, "Error: m and M must be positive integers.\n"); return 2; }
@@ -39,7 +40,7 @@ int main(int argc, char** argv) {
               D > 1 ? "Multi-GPU" : "Single-GPU", inst, tsb_taillard_nb_machines(inst), tsb_taillard_nb_jobs(inst),
               ub ? "opt" : "inf", lbs);
   tsb_search_stats st;
-  const int rc = tsb_pfsp_search(inst, lb, ub, m, M, D, &st);
+  const int rc = devpool ? tsb_pfsp_search_device(inst, lb, ub, m, M, D, &st) : tsb_pfsp_search(inst, lb, ub, m, M, D, &st);
   if (rc != TSB_OK) {
     std::fprintf(stderr, "tsb_pfsp_search: %s (%s)\n", tsb_strerror(rc), tsb_last_cuda_error());
     return 3;

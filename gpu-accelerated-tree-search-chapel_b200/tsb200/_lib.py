@@ -73,6 +73,13 @@ SYMBOLS = {
     "tsb_pfsp_destroy": (None, [_vp]),
     "tsb_pfsp_evaluate": (_i, [_vp, _i, _vp, _i, _i64, _vp]),
     "tsb_pfsp_evaluate_device": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
+    "tsb_pfsp_expand": (_i, [_vp, _i, _vp, _i, C.POINTER(_i64), _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
+    "tsb_pfsp_expand_device": (_i, [_vp, _i, _vp, _i, C.POINTER(_i64), _vp, C.POINTER(_u64), C.POINTER(_u64), _vp]),
+    "tsb_pfsp_pool_push": (_i, [_vp, _vp, _i64]),
+    "tsb_pfsp_pool_size": (_i64, [_vp]),
+    "tsb_pfsp_pool_step": (_i, [_vp, _i, _i, _i, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "tsb_pfsp_pool_drain": (_i, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    "tsb_pfsp_slow_rounds": (_u64, [_vp]),
     "tsb_pfsp_set_xfer": (_i, [_vp, _i]),
     "tsb_pfsp_kernel_launches": (_u64, [_vp]),
     "tsb_taillard_nb_jobs": (_i, [_i]),
@@ -83,6 +90,7 @@ SYMBOLS = {
     "tsb_nq_search": (_i, [_i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
     "tsb_nq_search_device": (_i, [_i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
     "tsb_pfsp_search": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
+    "tsb_pfsp_search_device": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
 }
 
 _lib = None

@@ -74,6 +74,55 @@ class PfspEvaluator:
               "tsb_pfsp_evaluate_device")
 
 
+    # ---- beyond the drop-in: fused evaluate_gpu + generate_children, device-resident pool
+    def expand(self, parents: np.ndarray, lb, best: int):
+        """(children, n_solutions, best_after): evaluate_gpu (pfsp_gpu_chpl.chpl:192-270) + generate_children
+        (:273-303) of one chunk in one device pass"""
+        assert parents.dtype == PFSP_NODE_DTYPE and parents.flags.c_contiguous
+        kind = LB_NAMES[lb] if isinstance(lb, str) else int(lb)
+        cap = parents.shape[0] * self.jobs
+        out = np.empty(max(cap, 1), dtype=PFSP_NODE_DTYPE)
+        nc, ns, b = C.c_uint64(0), C.c_uint64(0), C.c_int64(int(best))
+        check(lib().tsb_pfsp_expand(self._h, kind, parents.ctypes.data, parents.shape[0], C.byref(b), out.ctypes.data,
+                                    cap, C.byref(nc), C.byref(ns)), "tsb_pfsp_expand")
+        return out[: nc.value].copy(), int(ns.value), int(b.value)
+
+    def pool_push(self, nodes: np.ndarray) -> None:
+        assert nodes.dtype == PFSP_NODE_DTYPE and nodes.flags.c_contiguous
+        check(lib().tsb_pfsp_pool_push(self._h, nodes.ctypes.data, nodes.shape[0]), "tsb_pfsp_pool_push")
+
+    @property
+    def pool_size(self) -> int:
+        return int(lib().tsb_pfsp_pool_size(self._h))
+
+    @property
+    def slow_rounds(self) -> int:
+        return int(lib().tsb_pfsp_slow_rounds(self._h))
+
+    def pool_step(self, lb, m: int, M: int, best: int):
+        """(parents popped, children appended, solutions, best_after) of one device-side offload round"""
+        kind = LB_NAMES[lb] if isinstance(lb, str) else int(lb)
+        np_, nc, ns, b = C.c_int64(0), C.c_uint64(0), C.c_uint64(0), C.c_int64(int(best))
+        check(lib().tsb_pfsp_pool_step(self._h, kind, m, M, C.byref(b), C.byref(np_), C.byref(nc), C.byref(ns)),
+              "tsb_pfsp_pool_step")
+        return int(np_.value), int(nc.value), int(ns.value), int(b.value)
+
+    def pool_drain(self) -> np.ndarray:
+        n = self.pool_size
+        out = np.empty(max(n, 1), dtype=PFSP_NODE_DTYPE)
+        got = C.c_int64(0)
+        check(lib().tsb_pfsp_pool_drain(self._h, out.ctypes.data, n, C.byref(got)), "tsb_pfsp_pool_drain")
+        return out[: got.value].copy()
+
+
+def pfsp_search_device(inst: int = 14, lb="lb1", ub: int = 1, m: int = 25, M: int = 50000, D: int = 1) -> SearchStats:
+    """same search, the pool(s) of step 2 resident on the device(s) (tsb_pfsp_pool_*)"""
+    kind = LB_NAMES[lb] if isinstance(lb, str) else int(lb)
+    st = SearchStats()
+    check(lib().tsb_pfsp_search_device(inst, kind, ub, m, M, D, C.byref(st)), "tsb_pfsp_search_device")
+    return st
+
+
 def pfsp_search(inst: int = 14, lb="lb1", ub: int = 1, m: int = 25, M: int = 50000, D: int = 1) -> SearchStats:
     """pfsp_gpu_chpl.chpl:306-431 (D = 1) / pfsp_multigpu_chpl.chpl (static split), C++ emulation driver"""
     kind = LB_NAMES[lb] if isinstance(lb, str) else int(lb)

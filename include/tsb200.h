@@ -150,8 +150,28 @@ void tsb_pfsp_destroy(tsb_pfsp* h);
 int tsb_pfsp_evaluate(tsb_pfsp* h, int lb_kind, const void* parents, int count, int64_t best, int32_t* bounds);
 int tsb_pfsp_evaluate_device(tsb_pfsp* h, int lb_kind, const void* parents_d, int count, int64_t best,
                              int32_t* bounds_d, void* stream);
+/* ---- beyond the drop-in: fused evaluate + generate_children on the device, the PFSP twin
+ * of tsb_nq_expand*: evaluate_gpu (pfsp_gpu_chpl.chpl:192-270) followed by generate_children (:273-303) of one
+ * chunk.  *best is the incumbent: read at entry, lowered to the smallest leaf bound of the chunk exactly as
+ * the reference's sequential generate_children does (a round in which a leaf improves *best is redone through
+ * the evaluate entry point and the sequential rule, so the children are the reference's in every case).
+ * *n_solutions = evaluated leaf children (:283-288).  children come back packed, reference order. */
+int tsb_pfsp_expand(tsb_pfsp* h, int lb_kind, const void* parents, int count, int64_t* best, void* children,
+                    uint64_t capacity_nodes, uint64_t* n_children, uint64_t* n_solutions);
+int tsb_pfsp_expand_device(tsb_pfsp* h, int lb_kind, const void* parents_d /*16-B aligned*/, int count,
+                           int64_t* best, void* children_d /*8-B aligned*/, uint64_t* n_children,
+                           uint64_t* n_solutions, void* stream);
+/* ---- device-resident pool, the PFSP twin of tsb_nq_pool_*: one offload round of
+ * pfsp_gpu_chpl.chpl:376-392 (popBackBulk, evaluate, generate_children) per tsb_pfsp_pool_step, the pool kept
+ * in HBM and read in place */
+int tsb_pfsp_pool_push(tsb_pfsp* h, const void* nodes, int64_t n);
+int64_t tsb_pfsp_pool_size(const tsb_pfsp* h);
+int tsb_pfsp_pool_step(tsb_pfsp* h, int lb_kind, int m, int M, int64_t* best, int64_t* n_parents,
+                       uint64_t* n_children, uint64_t* n_solutions);
+int tsb_pfsp_pool_drain(tsb_pfsp* h, void* nodes, int64_t capacity_nodes, int64_t* n);
 int tsb_pfsp_set_xfer(tsb_pfsp* h, int mode);
 uint64_t tsb_pfsp_kernel_launches(const tsb_pfsp* h);
+uint64_t tsb_pfsp_slow_rounds(const tsb_pfsp* h); /* expand rounds redone on the host because a leaf improved best */
 
 /* ------------------------------------------------------------------ host-side problem data
  * (CPU code the Chapel drivers already own — lib/pfsp/Taillard.chpl, fill_* in Bound_*.chpl —
@@ -193,6 +213,8 @@ int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out);
 int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* out);
 /* pfsp_gpu_chpl.chpl:306-431 / pfsp_multigpu_chpl.chpl:316-560 */
 int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out);
+/* the same with the pool(s) of step 2 resident on the device(s) (tsb_pfsp_pool_*) */
+int tsb_pfsp_search_device(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,8 @@ def lib() -> C.CDLL:
         L.or_pfsp_evaluate_range.argtypes = [C.POINTER(Tables), i32, vp, i32, i32, i64, vp]
         L.or_nq_expand_chunk.argtypes = [vp, i32, i32, i32, vp, i64, C.POINTER(C.c_uint64)]
         L.or_nq_expand_chunk.restype = C.c_int64
+        L.or_pfsp_expand_chunk.argtypes = [vp, i32, vp, i32, C.POINTER(C.c_int64), vp, i64, C.POINTER(C.c_uint64)]
+        L.or_pfsp_expand_chunk.restype = C.c_int64
         L.or_nq_search_seq.argtypes = [i32, i32, C.POINTER(SearchResult)]
         L.or_nq_search_offload.argtypes = [i32, i32, i32, i32, i32, C.POINTER(SearchResult)]
         L.or_pfsp_search_seq.argtypes = [i32, i32, i32, i32, C.POINTER(SearchResult)]
@@ -140,6 +142,19 @@ def nq_expand(parents: np.ndarray, N: int, g: int = 1):
     sol = C.c_uint64(0)
     n = lib().or_nq_expand_chunk(_ptr(parents), parents.shape[0], N, g, _ptr(out), cap, C.byref(sol))
     return out[:n].copy(), int(sol.value)
+
+
+def pfsp_expand(t: Tables, lb_kind: int, parents: np.ndarray, best: int):
+    """(children, n_solutions, best_after) of one chunk: bounds with `best` at launch, then the reference's
+    sequential generate_children"""
+    assert parents.dtype == PFSP_NODE_DTYPE and parents.flags.c_contiguous
+    cap = parents.shape[0] * t.jobs + 1
+    out = np.zeros(cap, dtype=PFSP_NODE_DTYPE)
+    sol = C.c_uint64(0)
+    b = C.c_int64(int(best))
+    n = lib().or_pfsp_expand_chunk(C.byref(t), lb_kind, _ptr(parents), parents.shape[0], C.byref(b), _ptr(out), cap,
+                                   C.byref(sol))
+    return out[:n].copy(), int(sol.value), int(b.value)
 
 
 def nq_live_mask(parents: np.ndarray, N: int) -> np.ndarray:

@@ -739,6 +739,27 @@ static void pfsp_generate_children(int jobs, const or_pfsp_node* parents, int64_
   }
 }
 
+/* evaluate_gpu + generate_children of one PFSP chunk (pfsp_gpu_chpl.chpl:384-392): bounds with `best` at
+ * launch, then the sequential rule of generate_children (best lowered by leaves while the chunk is walked) */
+int64_t or_pfsp_expand_chunk(const or_pfsp_tables* t, int lb_kind, const or_pfsp_node* parents, int count,
+                             int64_t* best, or_pfsp_node* children, int64_t capacity, uint64_t* solutions) {
+  const int jobs = t->jobs;
+  int32_t* bounds = (int32_t*)malloc(((size_t)count * jobs + 1) * sizeof(int32_t));
+  or_pool pool;
+  pool_init(&pool, sizeof(or_pfsp_node));
+  uint64_t tree = 0, sol = 0;
+  memset(bounds, 0xCD, ((size_t)count * jobs + 1) * sizeof(int32_t));
+  or_pfsp_evaluate(t, lb_kind, parents, count, *best, bounds);
+  pfsp_generate_children(jobs, parents, count, bounds, &tree, &sol, best, &pool);
+  const int64_t n = pool.size;
+  if (n <= capacity && n > 0)
+    memcpy(children, pool.elements + (size_t)pool.front * pool.elt, (size_t)n * sizeof(or_pfsp_node));
+  if (solutions) *solutions = sol;
+  pool_free(&pool);
+  free(bounds);
+  return n;
+}
+
 /* pfsp_gpu_chpl.chpl:373-396: `best` is the value AT LAUNCH for the whole chunk */
 static void pfsp_offload_loop(const or_pfsp_tables* t, int lb_kind, int m, int M, or_pool* pool, int64_t* best,
                               or_search_result* r, or_pfsp_node* parents, int32_t* bounds, capture_t* cap) {

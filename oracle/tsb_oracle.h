@@ -85,6 +85,11 @@ void or_pfsp_evaluate_range(const or_pfsp_tables* t, int lb_kind, const or_pfsp_
 int64_t or_nq_expand_chunk(const or_nq_node* parents, int count, int N, int g, or_nq_node* children,
                            int64_t capacity, uint64_t* solutions);
 
+/* evaluate_gpu + generate_children of one PFSP chunk (pfsp_gpu_chpl.chpl:384-392, 273-303); *best is read at
+ * entry (value at launch for the bounds) and lowered by the leaves in the reference's sequential order */
+int64_t or_pfsp_expand_chunk(const or_pfsp_tables* t, int lb_kind, const or_pfsp_node* parents, int count,
+                             int64_t* best, or_pfsp_node* children, int64_t capacity, uint64_t* solutions);
+
 /* ---- whole searches ---- */
 typedef struct {
   uint64_t tree, sol;
