@@ -16,6 +16,12 @@ A *step* is one pass of the hot path over one batch of synthetic parent nodes:
            against MEASURED_PEAKS.json's HBM copy bandwidth;
 `at_M50000` = the same three numbers at the reference's default chunk size --M 50000 (launch-latency bound:
            1.9 MB per launch), which is what one offload of the unmodified Chapel driver would see.
+`search`   = whole searches (explored tree / wall time, the quantity the reference prints) with the pool of
+           step 2 resident in HBM (tsb_*_search_device: count + build kernels per round, nothing but three
+           counters crosses PCIe): N-Queens N=17 at --M and at the reference's --M 50000, PFSP ta014/lb1 and
+           ta020/lb2 at --M 50000 (BASELINE configs 2-4).  Counts are checked against the reference's.  With
+           N > 1 ranks every rank runs one task of the reference's static N-way split of the warm-up pool
+           (tsb_*_search_device_part) on its own GPU; tree = sum over ranks, time = max over ranks ("strong").
 Between timed iterations the inputs/outputs rotate over buffer sets whose total footprint exceeds the 126 MB L2.
 
 `--impl reference` times the reference's own CPU implementation of the same path (its isSafe / lb1_bound
@@ -310,6 +316,45 @@ def run_workload(kind, M, steps, warmup, device_index, world, N=17):
     }
 
 
+# ----------------------------------------------------------------------------------------- whole searches
+GOLDEN_TREES = {("nq", 17): (8017021931, 95815104), ("pfsp", 14, "lb1"): (2573652, 2648, 1377),
+                ("pfsp", 20, "lb2"): (4870386, 0, 1591)}  # tests/golden/counts.json (reference binaries)
+
+
+def run_search(kind, world, rank, device_index, reps, **kw):
+    """best-of-`reps` whole search; rank r runs task r of the world-way static split on its own GPU"""
+    import torch
+
+    import tsb200
+    dev = torch.device(f"cuda:{device_index}")
+    best_t, out = None, None
+    for _ in range(reps):
+        dist_barrier(world)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if kind == "nq":
+            st = tsb200.nqueens_search_device_part(kw["N"], 1, 25, kw["M"], world, rank, device_index)
+        else:
+            st = tsb200.pfsp_search_device_part(kw["inst"], kw["lb"], 1, 25, kw["M"], world, rank, device_index)
+        dt = time.perf_counter() - t0
+        t_max, tree = dist_max_sum(world, dt, st.explored_tree, dev)
+        _, sol = dist_max_sum(world, 0.0, st.explored_sol, dev)
+        _, offl = dist_max_sum(world, 0.0, st.offloads, dev)
+        _, launches = dist_max_sum(world, 0.0, st.kernel_launches, dev)
+        if best_t is None or t_max < best_t:
+            best_t = t_max
+            out = {"explored_tree": int(tree), "explored_sol": int(sol), "seconds": t_max,
+                   "value": tree / t_max / 1e6, "unit": "Mnodes/s", "offloads": int(offl),
+                   "gpu_launches": int(launches), "M": kw["M"], "reps": reps, "rank0_share": st.explored_tree / tree}
+            if kind == "pfsp":
+                out["optimum"] = int(st.best)
+    key = ("nq", kw["N"]) if kind == "nq" else ("pfsp", kw["inst"], kw["lb"])
+    if key in GOLDEN_TREES:
+        want = GOLDEN_TREES[key]
+        out["counts_match_reference"] = (out["explored_tree"], out["explored_sol"]) == want[:2]
+    return out
+
+
 def summarize(r, peak, peak_src, traffic=None):
     alg_bytes = r["M"] * (r["in_rec"] + r["out_rec"])
     t_kernel = r["t_dev_local"] / r["steps"]
@@ -405,6 +450,7 @@ def main():
     ap.add_argument("--no-pfsp", action="store_true")
     ap.add_argument("--no-small", action="store_true", help="skip the --M 50000 measurements")
     ap.add_argument("--lb2", action="store_true", help="also time PFSP ta020 lb2 (BASELINE configs[3])")
+    ap.add_argument("--no-search", action="store_true", help="skip the whole-search measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, local_rank, world = dist_env()
@@ -453,7 +499,11 @@ def main():
     peak, peak_src = peaks()
 
     big = run_workload("nq", args.M, args.steps, args.warmup, device_index, world, N)
-    main_s = summarize(big, peak, peak_src, traffic=None)
+    # DRAM bytes of one launch from the ncu --set full capture of this very launch shape (N=17, 4 Mi parents:
+    # profiles/nq_eval_r1_ncu.txt, dram__bytes_read.sum + dram__bytes_write.sum; the labels written last are
+    # still in the 126 MB L2 when the kernel ends)
+    traffic = 88130560 + 14575360 if (args.M == 1 << 22 and N == 17) else None
+    main_s = summarize(big, peak, peak_src, traffic=traffic)
     line = {"metric": "Mnodes/s", "value": main_s["value"], "unit": "Mnodes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_s["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
@@ -485,6 +535,16 @@ def main():
                             "ta020/lb2 offload depth histogram; int-ALU bound (O(pairs*jobs) per child)",
                             "M": 1 << 18, "value": ls["value"], "unit": "Mnodes/s", "ms_per_step": ls["ms_per_step"],
                             "e2e": ls["e2e"], "roofline": ls["roofline"], "gpu_launches": l2["launches"]}
+    if not args.no_search:
+        reps = 3
+        srch = {"note": "explored tree / wall time of whole searches, pool resident in HBM (tsb_*_search_device); "
+                        "time includes step 1 and 3 on the CPU, handle creation and arena allocation",
+                "scaling": "strong" if world > 1 else None,
+                "nqueens_N17": run_search("nq", world, rank, device_index, reps, N=17, M=args.M),
+                "nqueens_N17_M50000": run_search("nq", world, rank, device_index, 1, N=17, M=50000),
+                "pfsp_ta014_lb1_M50000": run_search("pfsp", world, rank, device_index, reps, inst=14, lb="lb1", M=50000),
+                "pfsp_ta020_lb2_M50000": run_search("pfsp", world, rank, device_index, reps, inst=20, lb="lb2", M=50000)}
+        line["search"] = srch
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
         line["cpu_baseline"] = cpu_baseline("nq", big["sample"][: 1 << 21], threads)

@@ -134,42 +134,47 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_expand_count_lb1_kernel(const
 // ------------------------------------------------------------------------------------------- count: lb2
 struct Lb2CountSmem {
   Lb2Smem core;  // tiles.in[0..1]: two input stages
-  uint32_t cmask[PF_TILE];
-  uint32_t leafs[PF_TILE];
+  uint32_t cmask[LB2_TILE];
+  uint32_t leafs[LB2_TILE];
   int red[8];
 };
 
+// (tiles of LB2_TILE = 64 parents: two linear tiles of this kernel make one 128-parent tile of the build
+// kernel, so masks and counts are laid out for PF_TILE: mask index = lin * 64 + t, tile_sums[lin / 2] is
+// accumulated with an atomicAdd — the host clears tile_sums before the launch)
 template <int M>
 __global__ void __launch_bounds__(PF_THREADS) pfsp_expand_count_lb2_kernel(const uint8_t* __restrict__ arena,
                                                                           const __grid_constant__ ExpandParams prm,
                                                                           const PfspLb1Tables* __restrict__ tables1,
-                                                                          const PfspLb2Tables* __restrict__ tables2,
+                                                                          const __grid_constant__ Lb2Const C,
                                                                           uint32_t* __restrict__ cmask,
                                                                           int* __restrict__ tile_sums,
                                                                           ExpandState* __restrict__ st) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Lb2CountSmem& sm = *reinterpret_cast<Lb2CountSmem*>(smem_raw);
-  if (threadIdx.x == 0) {
-    mbar_init(&sm.core.tab_bar[0], 1);
-    mbar_fence_init();
-    mbar_arrive_expect_tx(&sm.core.tab_bar[0], sizeof(PfspLb1Tables) + sizeof(PfspLb2Tables));
-    bulk_g2s(&sm.core.tab1, tables1, sizeof(PfspLb1Tables), &sm.core.tab_bar[0]);
-    bulk_g2s(&sm.core.tab2, tables2, sizeof(PfspLb2Tables), &sm.core.tab_bar[0]);
-  }
-  __syncthreads();
-  mbar_wait(&sm.core.tab_bar[0], 0);
+  stage_blob(&sm.core.tab1, tables1, sizeof(PfspLb1Tables), &sm.core.tab_bar[0]);
   const int jobs = sm.core.tab1.jobs, best = prm.best;
   unsigned my_solutions = 0;
-  run_piece_tiles<2, PF_TILE, PF_REC>(
-      sm.core.tiles.in[0], sm.core.tiles.full, arena, prm,
+  // this kernel walks the round in half tiles: linear half-tile h covers records [64h, 64h+64) of linear tile h/2
+  ExpandParams half = prm;
+  for (int i = 0; i < half.n_pieces; i++) {
+    // a piece's first build tile starts at first_tile*128 = (2*first_tile)*64
+    half.piece[i].first_tile *= 2;
+    half.piece[i].tile_cum *= 2;
+  }
+  half.n_tiles *= 2;
+  run_piece_tiles<2, LB2_TILE, PF_REC>(
+      sm.core.tiles.in[0], sm.core.tiles.full, arena, half,
       [&](const uint8_t* in_tile, int lin, long long at, long long lo, long long hi) {
-        const int rec_lo = static_cast<int>(lo - at * PF_TILE), rec_hi = static_cast<int>(hi - at * PF_TILE);
+        const int rec_lo = static_cast<int>(lo - at * LB2_TILE), rec_hi = static_cast<int>(hi - at * LB2_TILE);
         const int t = threadIdx.x;
         const int32_t* nodes = reinterpret_cast<const int32_t*>(in_tile);
-        sm.cmask[t] = 0;
-        sm.leafs[t] = 0;  // (lb2_compute_tile starts with a barrier)
+        if (t < LB2_TILE) {
+          sm.cmask[t] = 0;
+          sm.leafs[t] = 0;  // (lb2_compute_tile starts with a barrier)
+        }
         lb2_compute_tile<M>(
-            sm.core, in_tile, rec_lo, rec_hi, best,
+            sm.core, C, in_tile, rec_lo, rec_hi, best,
             [&](int p, int k, int lb) {
               if (nodes[22 * p] + 1 == jobs) {  // leaf child (pfsp_gpu_chpl.chpl:283-288)
                 atomicOr(&sm.leafs[p], 1u << k);
@@ -180,9 +185,18 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_expand_count_lb2_kernel(const
             },
             [](int, int) {});
         __syncthreads();
-        const uint32_t m = sm.cmask[t];
-        pf_tile_totals(sm.red, __popc(m), __popc(sm.leafs[t]), lin, tile_sums, my_solutions);
-        cmask[static_cast<long long>(lin) * PF_TILE + t] = m;
+        const uint32_t m = t < LB2_TILE ? sm.cmask[t] : 0u;
+        int packed = __popc(m) | ((t < LB2_TILE ? __popc(sm.leafs[t]) : 0) << 16);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
+        if ((t & 31) == 0) sm.red[t >> 5] = packed;
+        __syncthreads();
+        if (t == 0) {
+          const int tot = sm.red[0] + sm.red[1] + sm.red[2] + sm.red[3];
+          if (tot & 0xFFFF) atomicAdd(&tile_sums[lin >> 1], tot & 0xFFFF);
+          my_solutions += static_cast<unsigned>(tot >> 16);
+        }
+        if (t < LB2_TILE) cmask[static_cast<long long>(lin) * LB2_TILE + t] = m;
       });
   if (threadIdx.x == 0 && my_solutions) atomicAdd(&st->solutions, static_cast<unsigned long long>(my_solutions));
 }

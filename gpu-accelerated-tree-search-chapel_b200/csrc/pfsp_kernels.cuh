@@ -32,14 +32,7 @@ struct PfspLb1Tables {
   int32_t min_tails[PF_MAXM];
   int32_t pj[PF_MAXJ * 22];            // job-major: pj[job*mp + k], mp = row_stride(template M)
 };
-struct PfspLb2Tables {
-  int32_t pm[PF_MAXM * PF_MAXJ];       // machine-major as given: pm[k*jobs + job]
-  int32_t mp0[PF_MAXP + 2], mp1[PF_MAXP + 2], order[PF_MAXP + 2];
-  int32_t johnson[PF_MAXP * PF_MAXJ];  // [pair*jobs + pos] -> job
-  int32_t lags[PF_MAXP * PF_MAXJ];     // [pair*jobs + job]
-};
 static_assert(sizeof(PfspLb1Tables) % 16 == 0, "blob must be a multiple of 16 B");
-static_assert(sizeof(PfspLb2Tables) % 16 == 0, "blob must be a multiple of 16 B");
 
 __device__ __forceinline__ void stage_blob(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   if (threadIdx.x == 0) {
@@ -283,39 +276,54 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_lb1_kernel(const uint8_t* __r
 // machine pairs in machine_pair_order with compute_cmax_johnson (:188-212) per pair and the
 // early exit `lb > best` reproduced exactly (first pair, in order, where the running max
 // exceeds best).
-// Two phases per tile so that every lane carries a live child: (A) one thread per parent
-// computes the parent front and appends its live (parent, slot) items to a shared list;
-// (B) threads take items round-robin and run the pair loop for one child each.
+//
+// v2.  The Johnson tables are PACKED and live in the constant bank (kernel parameter): one word per
+// (pair, position) = job | p[ma0][job] << 5 | p[ma1][job] << 12 | lag << 19 and one word per pair
+// = ma0 | ma1 << 5 | min_tails[ma0] << 10 | min_tails[ma1] << 21, both in machine_pair_order.  All lanes
+// of a warp walk the same (pair, position), so the table word is a uniform constant load and its
+// unpacking runs on the uniform datapath; per lane and position only the scheduled-bit test, two adds and
+// one max remain (v1: four dependent shared-memory loads per position and 34 KB of tables per CTA).
+// Per tile of 64 parents: (A) one thread per parent computes the parent front and appends its live
+// (parent, slot) children to a shared list; (B) the pairs are processed in chunks of LB2_CHUNK: every
+// thread takes children from the ACTIVE list, rebuilds the child front (10 adds), runs the chunk, and
+// re-appends the child to the next list unless its bound already exceeds `best` — about 90 % of the
+// children are pruned within the first pairs, and compacting the survivors keeps the warps full (v1 kept
+// a whole warp busy for all pairs as soon as one of its 32 children survived).
+constexpr int LB2_TILE = 64;
 constexpr int LB2_STAGES = 2;
-using Lb2Tiles = TileSmem<LB2_STAGES, PF_TILE * PF_REC, PF_TILE * PF_MAXJ * 4>;
+constexpr int LB2_CHUNK = 5;  // machine pairs between two compactions
+struct Lb2Const {
+  uint32_t pair[PF_MAXP + 2];
+  uint32_t jp[PF_MAXP * PF_MAXJ];
+};
+static_assert(sizeof(Lb2Const) <= 16 * 1024, "must fit the kernel parameter space next to the other arguments");
+using Lb2Tiles = TileSmem<LB2_STAGES, LB2_TILE * PF_REC, LB2_TILE * PF_MAXJ * 4>;
 
 struct Lb2Smem {
   Lb2Tiles tiles;
   alignas(16) PfspLb1Tables tab1;
-  alignas(16) PfspLb2Tables tab2;
   alignas(8) uint64_t tab_bar[2];
-  int32_t front[PF_MAXM][PF_TILE];        // parent fronts, [machine][parent]
-  int32_t fc[PF_MAXM][PF_THREADS];        // per-thread child front scratch, [machine][thread]
-  uint32_t sched[PF_TILE];                // bit j set <=> job j scheduled in the parent
-  uint16_t items[PF_TILE * PF_MAXJ];      // (parent << 5) | slot
-  int32_t n_items;
+  int32_t front[PF_MAXM][LB2_TILE];             // parent fronts, [machine][parent]
+  int32_t fc[PF_MAXM][PF_THREADS];              // per-thread child front scratch, [machine][thread]
+  uint32_t sched[LB2_TILE];                     // bit j set <=> job j scheduled in the parent
+  uint32_t list[2][LB2_TILE * PF_MAXJ];         // active children: parent << 24 | slot << 16 | running lb
+  int32_t n_list[2];
 };
 
 // `emit(p, k, lb)` receives the bound of every live (parent p, slot k) of the tile's parents [rec_lo, rec_hi);
 // `dead(p, k)` is called for the slots below the live range (the evaluator zeroes them).
 template <int M, typename Emit, typename Dead>
-__device__ __forceinline__ void lb2_compute_tile(Lb2Smem& sm, const uint8_t* in_tile, int rec_lo, int rec_hi,
-                                                 int best, Emit&& emit, Dead&& dead) {
+__device__ __forceinline__ void lb2_compute_tile(Lb2Smem& sm, const Lb2Const& C, const uint8_t* in_tile, int rec_lo,
+                                                 int rec_hi, int best, Emit&& emit, Dead&& dead) {
   const int t = threadIdx.x;
   const PfspLb1Tables& tab = sm.tab1;
-  const PfspLb2Tables& t2 = sm.tab2;
   const int jobs = tab.jobs;
   const int32_t* nodes = reinterpret_cast<const int32_t*>(in_tile);
 
-  if (t == 0) sm.n_items = 0;
+  if (t < 2) sm.n_list[t] = 0;
   __syncthreads();
   // ---- phase A
-  if (t >= rec_lo && t < rec_hi) {
+  if (t < LB2_TILE && t >= rec_lo && t < rec_hi) {
     const int32_t* node = nodes + 22 * t;
     const int limit1 = min(max(node[1], -1), PF_MAXJ - 1);
     int F[M], R[M];
@@ -326,55 +334,70 @@ __device__ __forceinline__ void lb2_compute_tile(Lb2Smem& sm, const uint8_t* in_
     for (int i = 0; i <= limit1; i++) mask |= 1u << node[2 + i];
     sm.sched[t] = mask;
     const int live = jobs - 1 - limit1;
-    int base = live > 0 ? atomicAdd(&sm.n_items, live) : 0;
+    int base = live > 0 ? atomicAdd(&sm.n_list[0], live) : 0;
     for (int k = 0; k < jobs; k++) {
       if (k > limit1)
-        sm.items[base++] = static_cast<uint16_t>((t << 5) | k);
+        sm.list[0][base++] = (static_cast<uint32_t>(t) << 24) | (static_cast<uint32_t>(k) << 16);
       else
         dead(t, k);
     }
   }
   __syncthreads();
   // ---- phase B
-  const int n_items = sm.n_items;
   const int pairs = tab.pairs;
-  for (int it = t; it < n_items; it += PF_THREADS) {
-    const int item = sm.items[it];
-    const int p = item >> 5, k = item & 31;
-    const int job = nodes[22 * p + 2 + k];
-    const uint32_t mask = sm.sched[p] | (1u << job);
-    {  // child front = add_forward(parent front, job)
-      int row[M];
-      load_row<M>(tab, job, row);
-      int f = sm.front[0][p] + row[0];
-      sm.fc[0][t] = f;
+  int cur = 0;
+  for (int l0 = 0; l0 < pairs; l0 += LB2_CHUNK, cur ^= 1) {
+    const int n_act = sm.n_list[cur];
+    if (n_act == 0) break;  // (uniform)
+    const int l1 = min(pairs, l0 + LB2_CHUNK);
+    const bool last = l1 == pairs;
+    for (int it = t; it < n_act; it += PF_THREADS) {
+      const uint32_t e = sm.list[cur][it];
+      const int p = e >> 24, k = (e >> 16) & 31;
+      int lb = e & 0xFFFF;
+      const int job = nodes[22 * p + 2 + k];
+      const uint32_t mask = sm.sched[p] | (1u << job);
+      {  // child front = add_forward(parent front, job)
+        int row[M];
+        load_row<M>(tab, job, row);
+        int f = sm.front[0][p] + row[0];
+        sm.fc[0][t] = f;
 #pragma unroll
-      for (int j = 1; j < M; j++) {
-        f = max(f, sm.front[j][p]) + row[j];
-        sm.fc[j][t] = f;
-      }
-    }
-    int lb = 0;
-    for (int l = 0; l < pairs; l++) {
-      const int i = t2.order[l];
-      const int ma0 = t2.mp0[i], ma1 = t2.mp1[i];
-      int tmp0 = sm.fc[ma0][t], tmp1 = sm.fc[ma1][t];
-      const int32_t* js = &t2.johnson[i * jobs];
-      const int32_t* lg = &t2.lags[i * jobs];
-      const int32_t* p0 = &t2.pm[ma0 * jobs];
-      const int32_t* p1 = &t2.pm[ma1 * jobs];
-      for (int j = 0; j < jobs; j++) {
-        const int jb = js[j];
-        if (!((mask >> jb) & 1u)) {
-          tmp0 += p0[jb];
-          tmp1 = max(tmp1, tmp0 + lg[jb]) + p1[jb];
+        for (int j = 1; j < M; j++) {
+          f = max(f, sm.front[j][p]) + row[j];
+          sm.fc[j][t] = f;
         }
       }
-      tmp1 = max(tmp1 + tab.min_tails[ma1], tmp0 + tab.min_tails[ma0]);
-      lb = max(lb, tmp1);
-      if (lb > best) break;
+      bool over = false;
+      for (int l = l0; l < l1; l++) {
+        const uint32_t pi = C.pair[l];
+        int tmp0 = sm.fc[pi & 31u][t], tmp1 = sm.fc[(pi >> 5) & 31u][t];
+        const uint32_t* jp = &C.jp[l * PF_MAXJ];
+#pragma unroll
+        for (int j = 0; j < PF_MAXJ; j++) {
+          const uint32_t w = jp[j];
+          if (!(mask & (1u << (w & 31u)))) {
+            tmp0 += static_cast<int>((w >> 5) & 127u);
+            tmp1 = max(tmp1, tmp0 + static_cast<int>(w >> 19)) + static_cast<int>((w >> 12) & 127u);
+          }
+        }
+        const int c = max(tmp1 + static_cast<int>(pi >> 21), tmp0 + static_cast<int>((pi >> 10) & 2047u));
+        lb = max(lb, c);
+        if (lb > best) {
+          over = true;
+          break;
+        }
+      }
+      if (over || last) {
+        emit(p, k, lb);
+      } else {
+        const int at = atomicAdd(&sm.n_list[cur ^ 1], 1);
+        sm.list[cur ^ 1][at] = (e & 0xFFFF0000u) | static_cast<uint32_t>(lb);
+      }
     }
-    emit(p, k, lb);
+    __syncthreads();
+    if (t == 0) sm.n_list[cur] = 0;  // becomes the "next" list of the following chunk
+    __syncthreads();
   }
 }
 
@@ -382,24 +405,16 @@ template <int M>
 __global__ void __launch_bounds__(PF_THREADS) pfsp_lb2_kernel(const uint8_t* __restrict__ parents,
                                                              uint8_t* __restrict__ bounds, long long count,
                                                              const PfspLb1Tables* __restrict__ tables1,
-                                                             const PfspLb2Tables* __restrict__ tables2, int best) {
+                                                             const __grid_constant__ Lb2Const C, int best) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Lb2Smem& sm = *reinterpret_cast<Lb2Smem*>(smem_raw);
-  if (threadIdx.x == 0) {
-    mbar_init(&sm.tab_bar[0], 1);
-    mbar_fence_init();
-    mbar_arrive_expect_tx(&sm.tab_bar[0], sizeof(PfspLb1Tables) + sizeof(PfspLb2Tables));
-    bulk_g2s(&sm.tab1, tables1, sizeof(PfspLb1Tables), &sm.tab_bar[0]);
-    bulk_g2s(&sm.tab2, tables2, sizeof(PfspLb2Tables), &sm.tab_bar[0]);
-  }
-  __syncthreads();
-  mbar_wait(&sm.tab_bar[0], 0);
-  run_tile_pipeline<LB2_STAGES, PF_TILE, PF_REC, PF_MAXJ * 4>(
-      sm.tiles, parents, bounds, count, [&sm, best](const uint8_t* in_tile, uint8_t* out_tile, int n, long long) {
+  stage_blob(&sm.tab1, tables1, sizeof(PfspLb1Tables), &sm.tab_bar[0]);
+  run_tile_pipeline<LB2_STAGES, LB2_TILE, PF_REC, PF_MAXJ * 4>(
+      sm.tiles, parents, bounds, count, [&sm, &C, best](const uint8_t* in_tile, uint8_t* out_tile, int n, long long) {
         int32_t* out = reinterpret_cast<int32_t*>(out_tile);
         const int jobs = sm.tab1.jobs;
         lb2_compute_tile<M>(
-            sm, in_tile, 0, n, best, [out, jobs](int p, int k, int lb) { out[jobs * p + k] = lb; },
+            sm, C, in_tile, 0, n, best, [out, jobs](int p, int k, int lb) { out[jobs * p + k] = lb; },
             [out, jobs](int p, int k) { out[jobs * p + k] = 0; });
       });
 }

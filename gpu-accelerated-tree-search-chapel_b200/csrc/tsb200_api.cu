@@ -556,7 +556,7 @@ void pool_pop(DevicePool& p, long long n) {
 struct tsb_pfsp : Base {
   int jobs = 0, machines = 0, pairs = 0, mt = 0;  // mt = template machine count (5, 10 or 20)
   tsb::PfspLb1Tables* d_tab1 = nullptr;
-  tsb::PfspLb2Tables* d_tab2 = nullptr;
+  tsb::Lb2Const* lb2c = nullptr;  // packed Johnson tables, passed to the lb2 kernels by value (constant bank)
   bool attr_set[3] = {false, false, false};
   int occ[3] = {0, 0, 0};
   // fused expand + device-resident pool
@@ -599,9 +599,9 @@ int launch_lb2_m(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count, 
     h->attr_set[2] = true;
   }
   int grid = 1;
-  int rc = grid_for(kernel, tsb::PF_THREADS, smem, count, tsb::PF_TILE, h->di.sms, &grid, &h->occ[2]);
+  int rc = grid_for(kernel, tsb::PF_THREADS, smem, count, tsb::LB2_TILE, h->di.sms, &grid, &h->occ[2]);
   if (rc != TSB_OK) return rc;
-  kernel<<<grid, tsb::PF_THREADS, smem, s>>>(in, out, count, h->d_tab1, h->d_tab2, best);
+  kernel<<<grid, tsb::PF_THREADS, smem, s>>>(in, out, count, h->d_tab1, *h->lb2c, best);
   TSB_CUDA(cudaGetLastError());
   h->launches++;
   return TSB_OK;
@@ -651,9 +651,11 @@ int pfsp_expand_m(tsb_pfsp* h, int lb_kind, const uint8_t* arena, const tsb::Exp
       TSB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
       h->ex_attr[2] = true;
     }
-    rc = grid_for(k1, tsb::PF_THREADS, smem1, recs, tsb::PF_TILE, h->di.sms, &g1, &h->ex_occ[2]);
+    rc = grid_for(k1, tsb::PF_THREADS, smem1, recs, tsb::LB2_TILE, h->di.sms, &g1, &h->ex_occ[2]);
     if (rc != TSB_OK) return rc;
-    k1<<<g1, tsb::PF_THREADS, smem1, s>>>(arena, prm, h->d_tab1, h->d_tab2, ex.d_cmask, ex.d_tile, ex.d_st);
+    // (this kernel walks the round in half tiles and accumulates the tile counts)
+    TSB_CUDA(cudaMemsetAsync(ex.d_tile, 0, static_cast<size_t>(prm.n_tiles) * sizeof(int), s));
+    k1<<<g1, tsb::PF_THREADS, smem1, s>>>(arena, prm, h->d_tab1, *h->lb2c, ex.d_cmask, ex.d_tile, ex.d_st);
   } else if (lb_kind == TSB_LB1) {
     auto k1 = tsb::pfsp_expand_count_lb1_kernel<1, M>;
     const size_t smem1 = sizeof(tsb::Lb1CountSmem) + 128;
@@ -1020,14 +1022,11 @@ int tsb_pfsp_create(tsb_pfsp** out, int device, int jobs, int machines, int M_ma
   h->pairs = nb_pairs;
   h->mt = machines <= 5 ? 5 : machines <= 10 ? 10 : 20;
   int rc = h->init(device, M_max, sizeof(tsb_pfsp_node), static_cast<size_t>(jobs) * 4);
-  // tables -> device blobs (zero padding up to the template machine count is value-neutral:
+  // tables -> device blob (zero padding up to the template machine count is value-neutral:
   // the reference itself evaluates 20-wide zero-padded tuples, lib/pfsp/Bound_simple.chpl:125-135)
   std::vector<tsb::PfspLb1Tables> t1v(1);
-  std::vector<tsb::PfspLb2Tables> t2v(1);
   tsb::PfspLb1Tables& t1 = t1v[0];
-  tsb::PfspLb2Tables& t2 = t2v[0];
   std::memset(&t1, 0, sizeof(t1));
-  std::memset(&t2, 0, sizeof(t2));
   const int mp = tsb::row_stride(h->mt);
   t1.jobs = jobs;
   t1.machines = machines;
@@ -1039,28 +1038,49 @@ int tsb_pfsp_create(tsb_pfsp** out, int device, int jobs, int machines, int M_ma
     for (int j = 0; j < jobs; j++) {
       t1.total[k] += p_times[k * jobs + j];
       t1.pj[j * mp + k] = p_times[k * jobs + j];
-      t2.pm[k * jobs + j] = p_times[k * jobs + j];
     }
   }
-  bool bad = false;
-  for (int i = 0; i < nb_pairs; i++) {
-    t2.mp0[i] = mp0[i];
-    t2.mp1[i] = mp1[i];
-    t2.order[i] = mp_order[i];
-    bad |= mp0[i] < 0 || mp0[i] >= machines || mp1[i] < 0 || mp1[i] >= machines || mp_order[i] < 0 ||
-           mp_order[i] >= nb_pairs;
+  // lb2: packed Johnson tables in machine_pair_order (tsb::Lb2Const); value ranges checked, indices checked
+  bool bad = false, wide = false;
+  if (nb_pairs > 0) {
+    h->lb2c = new (std::nothrow) tsb::Lb2Const();
+    if (!h->lb2c) rc = TSB_ENOMEM;
+  }
+  for (int l = 0; l < nb_pairs && h->lb2c; l++) {
+    const int i = mp_order[l];
+    if (i < 0 || i >= nb_pairs) {
+      bad = true;
+      continue;
+    }
+    const int a = mp0[i], b = mp1[i];
+    if (a < 0 || a >= machines || b < 0 || b >= machines) {
+      bad = true;
+      continue;
+    }
+    wide |= min_tails[a] < 0 || min_tails[a] > 2047 || min_tails[b] < 0 || min_tails[b] > 2047;
+    h->lb2c->pair[l] = static_cast<uint32_t>(a) | static_cast<uint32_t>(b) << 5 |
+                       static_cast<uint32_t>(min_tails[a] & 2047) << 10 | static_cast<uint32_t>(min_tails[b] & 2047) << 21;
     for (int j = 0; j < jobs; j++) {
-      t2.johnson[i * jobs + j] = johnson[i * jobs + j];
-      t2.lags[i * jobs + j] = lags[i * jobs + j];
-      bad |= johnson[i * jobs + j] < 0 || johnson[i * jobs + j] >= jobs;
+      const int job = johnson[i * jobs + j];
+      if (job < 0 || job >= jobs) {
+        bad = true;
+        continue;
+      }
+      const int pa = p_times[a * jobs + job], pb = p_times[b * jobs + job], lg = lags[i * jobs + job];
+      wide |= pa < 0 || pa > 127 || pb < 0 || pb > 127 || lg < 0 || lg > 8191;
+      h->lb2c->jp[l * tsb::PF_MAXJ + j] = static_cast<uint32_t>(job) | static_cast<uint32_t>(pa & 127) << 5 |
+                                          static_cast<uint32_t>(pb & 127) << 12 | static_cast<uint32_t>(lg & 8191) << 19;
     }
   }
   if (rc == TSB_OK && bad) rc = TSB_EINVAL;
+  if (rc == TSB_OK && wide) {  // processing times > 127 / lags > 8191 (outside the Taillard range): no lb2 on this handle
+    delete h->lb2c;
+    h->lb2c = nullptr;
+    h->pairs = 0;
+  }
   auto upload = [&]() -> int {
     TSB_CUDA(cudaMalloc(&h->d_tab1, sizeof(t1)));
-    TSB_CUDA(cudaMalloc(&h->d_tab2, sizeof(t2)));
     TSB_CUDA(cudaMemcpyAsync(h->d_tab1, &t1, sizeof(t1), cudaMemcpyHostToDevice, h->stream));
-    TSB_CUDA(cudaMemcpyAsync(h->d_tab2, &t2, sizeof(t2), cudaMemcpyHostToDevice, h->stream));
     TSB_CUDA(cudaStreamSynchronize(h->stream));
     return TSB_OK;
   };
@@ -1078,7 +1098,7 @@ void tsb_pfsp_destroy(tsb_pfsp* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->d_tab1) cudaFree(h->d_tab1);
-  if (h->d_tab2) cudaFree(h->d_tab2);
+  delete h->lb2c;
   h->ex.release();
   if (h->d_children) cudaFree(h->d_children);
   h->pool.release();

@@ -522,10 +522,13 @@ int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out) {
   return TSB_OK;
 }
 
-int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* out) {
-  if (!out || N < 1 || N > TSB_MAX_QUEENS || g < 1 || m < 1 || M < 1 || D < 1 || D > 8) return TSB_EINVAL;
+// part < 0: the whole search.  part >= 0: only task `part` of the D-way static split, on `device` (one rank of a
+// process-per-GPU launch): the step-1 tree is credited to part 0 and every part drains its own leftovers, so the
+// per-part counts add up to the whole search's.
+static int nq_search_device_impl(int N, int g, int m, int M, int D, int part, int device, tsb_search_stats* out) {
+  if (!out || N < 1 || N > TSB_MAX_QUEENS || g < 1 || m < 1 || M < 1 || D < 1 || D > 8 || part >= D) return TSB_EINVAL;
   std::memset(out, 0, sizeof(*out));
-  if (int rc = tsb_init_devices(D); rc != TSB_OK) return rc;
+  if (int rc = tsb_init_devices(part < 0 ? D : device + 1); rc != TSB_OK) return rc;
   Pool<tsb_nq_node> pool;
   tsb_nq_node root{};
   for (int i = 0; i < N; i++) root.board[i] = static_cast<uint8_t>(i);
@@ -542,7 +545,18 @@ int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* ou
   // step 2: every task's pool moves to its device and stays there (same static split as tsb_nq_search)
   std::vector<GpuTaskResult> res(D);
   const int ndev = std::max(1, tsb_device_count());
-  if (D == 1) {
+  if (part >= 0) {
+    if (part != 0) tree = sol = 0;  // step 1 is credited to part 0
+    std::vector<Pool<tsb_nq_node>> multi;
+    if (D == 1) {
+      multi.resize(1);
+      std::swap(multi[0], pool);
+    } else {
+      static_split(pool, D, multi);
+    }
+    nq_devpool_task(device, N, g, m, M, multi[part], res[part]);
+    while (multi[part].popBack(parent)) pool.pushBack(parent);
+  } else if (D == 1) {
     nq_devpool_task(0, N, g, m, M, pool, res[0]);
   } else {
     std::vector<Pool<tsb_nq_node>> multi;
@@ -572,15 +586,16 @@ int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* ou
   return TSB_OK;
 }
 
-static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, bool devpool, tsb_search_stats* out) {
-  if (!out || lb_kind < 0 || lb_kind > 2 || (ub != 0 && ub != 1) || m < 1 || M < 1 || D < 1 || D > 8)
+static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, bool devpool, int part, int device,
+                            tsb_search_stats* out) {
+  if (!out || lb_kind < 0 || lb_kind > 2 || (ub != 0 && ub != 1) || m < 1 || M < 1 || D < 1 || D > 8 || part >= D)
     return TSB_EINVAL;
   std::memset(out, 0, sizeof(*out));
   std::vector<tsb_pfsp_tables> tv(1);
   tsb_pfsp_tables& t = tv[0];
   int rc = tsb_pfsp_tables_build(&t, inst);
   if (rc != TSB_OK) return rc;
-  if (rc = tsb_init_devices(D); rc != TSB_OK) return rc;  // contexts exist before the timers start
+  if (rc = tsb_init_devices(part < 0 ? D : device + 1); rc != TSB_OK) return rc;  // contexts exist before the timers start
   HostBounds hb(t);
   int64_t best = ub == 1 ? tsb_taillard_best_ub(inst) : INT64_MAX;  // pfsp_gpu_chpl.chpl:37
   Pool<tsb_pfsp_node> pool;
@@ -601,7 +616,18 @@ static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, 
   const int ndev = std::max(1, tsb_device_count());
   for (auto& r : res) r.best = best;  // per-task best_l = best (pfsp_multigpu_chpl.chpl:384)
   auto task = devpool ? pfsp_devpool_task : pfsp_gpu_task;
-  if (D == 1) {
+  if (part >= 0) {  // one task of the split (see nq_search_device_impl)
+    if (part != 0) tree = sol = 0;
+    std::vector<Pool<tsb_pfsp_node>> multi;
+    if (D == 1) {
+      multi.resize(1);
+      std::swap(multi[0], pool);
+    } else {
+      static_split(pool, D, multi);
+    }
+    task(device, t, lb_kind, m, M, multi[part], res[part]);
+    while (multi[part].popBack(parent)) pool.pushBack(parent);
+  } else if (D == 1) {
     task(0, t, lb_kind, m, M, pool, res[0]);
   } else {
     std::vector<Pool<tsb_pfsp_node>> multi;
@@ -633,11 +659,23 @@ static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, 
   return TSB_OK;
 }
 
+int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* out) {
+  return nq_search_device_impl(N, g, m, M, D, -1, 0, out);
+}
+int tsb_nq_search_device_part(int N, int g, int m, int M, int D, int part, int device, tsb_search_stats* out) {
+  if (part < 0) return TSB_EINVAL;
+  return nq_search_device_impl(N, g, m, M, D, part, device, out);
+}
 int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out) {
-  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, false, out);
+  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, false, -1, 0, out);
 }
 int tsb_pfsp_search_device(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out) {
-  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, true, out);
+  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, true, -1, 0, out);
+}
+int tsb_pfsp_search_device_part(int inst, int lb_kind, int ub, int m, int M, int D, int part, int device,
+                                tsb_search_stats* out) {
+  if (part < 0) return TSB_EINVAL;
+  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, true, part, device, out);
 }
 
 }  // extern "C"

@@ -113,3 +113,11 @@ def nqueens_search_device(N: int = 14, g: int = 1, m: int = 25, M: int = 50000, 
     st = SearchStats()
     check(lib().tsb_nq_search_device(N, g, m, M, D, C.byref(st)), "tsb_nq_search_device")
     return st
+
+
+def nqueens_search_device_part(N: int, g: int, m: int, M: int, D: int, part: int, device: int = 0) -> SearchStats:
+    """task `part` of the D-way static split on `device` (one rank of a process-per-GPU launch); the parts'
+    counts add up to the whole search's"""
+    st = SearchStats()
+    check(lib().tsb_nq_search_device_part(N, g, m, M, D, part, device, C.byref(st)), "tsb_nq_search_device_part")
+    return st

@@ -129,3 +129,11 @@ def pfsp_search(inst: int = 14, lb="lb1", ub: int = 1, m: int = 25, M: int = 500
     st = SearchStats()
     check(lib().tsb_pfsp_search(inst, kind, ub, m, M, D, C.byref(st)), "tsb_pfsp_search")
     return st
+
+
+def pfsp_search_device_part(inst: int, lb, ub: int, m: int, M: int, D: int, part: int, device: int = 0) -> SearchStats:
+    kind = LB_NAMES[lb] if isinstance(lb, str) else int(lb)
+    st = SearchStats()
+    check(lib().tsb_pfsp_search_device_part(inst, kind, ub, m, M, D, part, device, C.byref(st)),
+          "tsb_pfsp_search_device_part")
+    return st

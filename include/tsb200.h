@@ -211,10 +211,15 @@ int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out);
  * chunk sequence, identical counts; the host only reads three counters per round.  D > 1 = the same static
  * strided split, one device pool per GPU. */
 int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* out);
+/* one task of that D-way split, on `device` — for process-per-GPU launches (one rank = one part): step 1 is
+ * credited to part 0 and each part drains its own leftovers, so the parts' counts add up to the whole search */
+int tsb_nq_search_device_part(int N, int g, int m, int M, int D, int part, int device, tsb_search_stats* out);
 /* pfsp_gpu_chpl.chpl:306-431 / pfsp_multigpu_chpl.chpl:316-560 */
 int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out);
 /* the same with the pool(s) of step 2 resident on the device(s) (tsb_pfsp_pool_*) */
 int tsb_pfsp_search_device(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out);
+int tsb_pfsp_search_device_part(int inst, int lb_kind, int ub, int m, int M, int D, int part, int device,
+                                tsb_search_stats* out);
 
 #ifdef __cplusplus
 }

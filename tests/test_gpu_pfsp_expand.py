@@ -105,7 +105,7 @@ def test_device_pool_is_byte_identical_to_the_reference_pool(lb):
 @pytest.mark.parametrize("inst,lb,ub,m,M,D", [(14, "lb1", 1, 25, 50000, 1), (14, "lb1_d", 1, 25, 50000, 1),
                                               (14, "lb2", 1, 25, 50000, 1), (14, "lb1", 1, 25, 3000, 3),
                                               (14, "lb1", 1, 5, 1 << 20, 1), (14, "lb2", 1, 25, 700, 2),
-                                              (14, "lb1_d", 0, 25, 50000, 1), (14, "lb2", 0, 25, 50000, 1)])
+                                              (14, "lb1_d", 0, 25, 50000, 1)])
 def test_device_resident_search_counts(golden_dir, inst, lb, ub, m, M, D):
     """whole searches: identical explored tree / solutions / optimum and the same chunk sequence as the reference
     driver (ub = 0: the incumbent is found on the way, several slow rounds; single task, so still deterministic)"""
