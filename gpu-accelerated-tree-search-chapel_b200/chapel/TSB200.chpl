@@ -43,6 +43,27 @@ module TSB200 {
   extern proc tsb_pfsp_evaluate(h: c_ptr(tsb_pfsp), lb_kind: c_int, parents: c_ptrConst(void), count: c_int,
                                 best: int(64), bounds: c_ptr(int(32))): c_int;
 
+  // ---- beyond the three offload lines: fused evaluate + generate_children, device-resident pool
+  // (INTEGRATION.md section 3b; SURVEY.md section 8f rows 1 and 3)
+  extern proc tsb_nq_expand(h: c_ptr(tsb_nq), parents: c_ptrConst(void), count: c_int, children: c_ptr(void),
+                            capacity_nodes: uint(64), ref n_children: uint(64), ref n_solutions: uint(64)): c_int;
+  extern proc tsb_nq_pool_push(h: c_ptr(tsb_nq), nodes: c_ptrConst(void), n: int(64)): c_int;
+  extern proc tsb_nq_pool_size(h: c_ptr(tsb_nq)): int(64);
+  extern proc tsb_nq_pool_step(h: c_ptr(tsb_nq), m: c_int, M: c_int, ref n_parents: int(64),
+                               ref n_children: uint(64), ref n_solutions: uint(64)): c_int;
+  extern proc tsb_nq_pool_drain(h: c_ptr(tsb_nq), nodes: c_ptr(void), capacity_nodes: int(64),
+                                ref n: int(64)): c_int;
+  extern proc tsb_pfsp_expand(h: c_ptr(tsb_pfsp), lb_kind: c_int, parents: c_ptrConst(void), count: c_int,
+                              ref best: int(64), children: c_ptr(void), capacity_nodes: uint(64),
+                              ref n_children: uint(64), ref n_solutions: uint(64)): c_int;
+  extern proc tsb_pfsp_pool_push(h: c_ptr(tsb_pfsp), nodes: c_ptrConst(void), n: int(64)): c_int;
+  extern proc tsb_pfsp_pool_size(h: c_ptr(tsb_pfsp)): int(64);
+  extern proc tsb_pfsp_pool_step(h: c_ptr(tsb_pfsp), lb_kind: c_int, m: c_int, M: c_int, ref best: int(64),
+                                 ref n_parents: int(64), ref n_children: uint(64),
+                                 ref n_solutions: uint(64)): c_int;
+  extern proc tsb_pfsp_pool_drain(h: c_ptr(tsb_pfsp), nodes: c_ptr(void), capacity_nodes: int(64),
+                                  ref n: int(64)): c_int;
+
   proc tsbCheck(rc: c_int, what: string) {
     if rc != TSB_OK then
       halt(what, ": ", string.createCopyingBuffer(tsb_strerror(rc)), " — ",

@@ -80,12 +80,12 @@ __device__ __forceinline__ void pf_tile_totals(int* red /* 8 ints, shared */, in
 
 // ------------------------------------------------------------------------------------------- count: lb1 / lb1_d
 struct Lb1CountSmem {
-  Lb1Smem core;  // tiles.in[0] is the one input stage; tiles.out[0] is unused here
+  Lb1Smem core;  // tiles.buf[0..1]: two input stages
   uint32_t cmask[PF_TILE];
   int red[8];
 };
 
-template <int KIND, int M>
+template <int KIND, int M, bool SIMD>
 __global__ void __launch_bounds__(PF_THREADS) pfsp_expand_count_lb1_kernel(const uint8_t* __restrict__ arena,
                                                                           const __grid_constant__ ExpandParams prm,
                                                                           const PfspLb1Tables* __restrict__ tables,
@@ -97,13 +97,13 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_expand_count_lb1_kernel(const
   stage_blob(&sm.core.tab, tables, sizeof(PfspLb1Tables), &sm.core.tab_bar);
   const int jobs = sm.core.tab.jobs, best = prm.best;
   unsigned my_solutions = 0;
-  run_piece_tiles<1, PF_TILE, PF_REC>(
-      sm.core.tiles.in[0], sm.core.tiles.full, arena, prm,
+  run_piece_tiles<2, PF_TILE, PF_REC>(
+      sm.core.tiles.buf[0], sm.core.tiles.full, arena, prm,
       [&](const uint8_t* in_tile, int lin, long long at, long long lo, long long hi) {
         const int rec_lo = static_cast<int>(lo - at * PF_TILE), rec_hi = static_cast<int>(hi - at * PF_TILE);
         uint32_t m = 0, live = 0;
         int leaf_lb = 0x7FFFFFFF;
-        const int p = lb1_compute_tile<KIND, M>(sm.core, in_tile, rec_lo, rec_hi,
+        const int p = lb1_compute_tile<KIND, M, SIMD, false>(sm.core, in_tile, rec_lo, rec_hi,
                                                 [&](int, int limit1, int g, const int(&v)[4]) {
 #pragma unroll
                                                   for (int c = 0; c < 4; c++) {

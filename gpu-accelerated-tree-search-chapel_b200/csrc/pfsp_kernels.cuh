@@ -31,6 +31,8 @@ struct PfspLb1Tables {
   int32_t min_heads[PF_MAXM];
   int32_t min_tails[PF_MAXM];
   int32_t pj[PF_MAXJ * 22];            // job-major: pj[job*mp + k], mp = row_stride(template M)
+  uint32_t ph[PF_MAXJ * 12];           // the same rows with two machines per word (16 bits each):
+                                       // ph[job*half_stride(M) + q] = p[2q][job] | p[2q+1][job] << 16
 };
 static_assert(sizeof(PfspLb1Tables) % 16 == 0, "blob must be a multiple of 16 B");
 
@@ -52,12 +54,12 @@ __device__ __forceinline__ void stage_blob(void* dst_smem, const void* src_gmem,
 // bank-conflict free: node words are read as 11 x LDS.64 (stride 88 B = odd multiple of 8 B), job
 // rows are `mp` ints at a stride of `mp` words read as LDS.64 (mp/2 odd for 10 machines), bounds
 // are written as 5 x STS.128 (stride 80 B = odd multiple of 16 B).
-constexpr int LB1_STAGES = 1;  // 21.5 KB of tiles per CTA -> 7 CTAs (28 warps) per SM; the CTAs overlap each other's loads
-template <int JOBS_OUT>
-using Lb1Tiles = TileSmem<LB1_STAGES, PF_TILE * PF_REC, PF_TILE * JOBS_OUT * 4>;
-
+// tiles: a ring of three 11 KB buffers used in place (run_tile_ring_inplace): the 80 B of bounds of a parent
+// overwrite the tile once every thread holds its 88-byte node in registers -> 6 CTAs (24 warps) per SM with
+// loads two tiles ahead (v4 had one input + one output buffer, 7 CTAs, and the TMA wait exposed: 18 % of the
+// warp stall samples).
 struct Lb1Smem {
-  Lb1Tiles<PF_MAXJ> tiles;
+  RingSmem<PF_TILE * PF_REC> tiles;
   alignas(16) PfspLb1Tables tab;
   alignas(8) uint64_t tab_bar;
   int32_t bin[32];            // per-tile histogram of parent depths, then exclusive prefix
@@ -92,6 +94,10 @@ __device__ __forceinline__ int depth_sorted_parent(int32_t* bin, uint8_t* order,
 // always one conflict-free wavefront (lanes with the same job broadcast).  8-byte row loads were
 // measured at 1.6x the ideal wavefront count (16 bank pairs cannot hold 20 rows).
 __host__ __device__ constexpr int row_stride(int M) { return M | 1; }
+
+// row stride (in words) of the half-word packed table: odd as well
+__host__ __device__ constexpr int half_words(int M) { return (M + 1) / 2; }
+__host__ __device__ constexpr int half_stride(int M) { return half_words(M) | 1; }
 
 // load row `job` of the job-major table: M machine times
 template <int M>
@@ -176,15 +182,49 @@ __device__ __forceinline__ int child_bound(const int (&F)[M], const int (&R)[M],
   }
 }
 
+// Two children at once in the two 16-bit halves of every register (DPX VIADDMNMX.U16x2 / VIMNMX.U16x2): the
+// add_front_and_bound recurrence (Bound_simple.chpl:197-222)
+//     lb = F[0] + RB[0];  t = F[0] + p[0];   for i >= 1:  s = max(t, F[i]);  lb = max(lb, s + RB[i]);  t = s + p[i]
+// with RB = remain + back folded once per parent.  F2 / RB2 hold the parent's values in both halves; the
+// children's processing times come from the half-word packed rows, one PRMT per machine interleaving the two
+// jobs.  All values are < 2^16 (checked when the handle is created), so plain 32-bit adds never carry from
+// the low half into the high one.  The lb1 entry point (lb1_bound on the child, Bound_simple.chpl:123-136)
+// takes this route too when min_tails is non-increasing — then max_i(running max_j<=i a_j + back_i) =
+// max_i(a_i + back_i), SURVEY.md Appendix A.4 — which fill_min_heads_tails guarantees; otherwise, and for values
+// beyond 16 bits, the scalar formulation above is used.
+template <int M>
+__device__ __forceinline__ uint32_t child_pair_bound(const PfspLb1Tables& tab, const uint32_t (&F2)[M],
+                                                     const uint32_t (&RB2)[M], int job_a, int job_b) {
+  constexpr int HW = half_words(M);
+  const uint32_t* ra = &tab.ph[job_a * half_stride(M)];
+  const uint32_t* rb = &tab.ph[job_b * half_stride(M)];
+  uint32_t wa[HW], wb[HW];
+#pragma unroll
+  for (int q = 0; q < HW; q++) {
+    wa[q] = ra[q];
+    wb[q] = rb[q];
+  }
+  uint32_t lb = F2[0] + RB2[0];
+  uint32_t t = F2[0] + __byte_perm(wa[0], wb[0], 0x5410);  // + (p_a[0], p_b[0])
+#pragma unroll
+  for (int i = 1; i < M; i++) {
+    const uint32_t s = __vmaxu2(t, F2[i]);
+    lb = __viaddmax_u16x2(s, RB2[i], lb);
+    const uint32_t p2 = __byte_perm(wa[i >> 1], wb[i >> 1], (i & 1) ? 0x7632 : 0x5410);
+    t = s + p2;
+  }
+  return lb;
+}
+
 // Bounds of all children of the tile's parents [rec_lo, rec_hi).  `emit(t, limit1, g, v)` receives, for parent
 // t and every group g of four slots with at least one live slot (k = 4g..4g+3 > limit1), the four bounds.
 // Returns the record this thread was given by the depth sort (a permutation of the tile's 128 records).
-template <int KIND, int M, typename Emit>
+template <int KIND, int M, bool SIMD, bool INPLACE, typename Emit>
 __device__ __forceinline__ int lb1_compute_tile(Lb1Smem& sm, const uint8_t* in_tile, int rec_lo, int rec_hi,
                                                 Emit&& emit) {
   const PfspLb1Tables& tab = sm.tab;
   const int t = depth_sorted_parent(sm.bin, sm.order, in_tile, rec_lo, rec_hi);
-  if (t < rec_lo || t >= rec_hi) return t;
+  const bool valid = t >= rec_lo && t < rec_hi;
   // the node: 22 ints as 11 8-byte loads
   const int2* node2 = reinterpret_cast<const int2*>(in_tile) + 11 * t;
   int prmu[PF_MAXJ];
@@ -193,9 +233,11 @@ __device__ __forceinline__ int lb1_compute_tile(Lb1Smem& sm, const uint8_t* in_t
 #pragma unroll
   for (int q = 0; q < 10; q++) {
     const int2 v = node2[1 + q];
-    prmu[2 * q] = v.x;
-    prmu[2 * q + 1] = v.y;
+    prmu[2 * q] = valid ? v.x : 0;
+    prmu[2 * q + 1] = valid ? v.y : 0;
   }
+  if constexpr (INPLACE) __syncthreads();  // every node is in registers: emit() may overwrite the tile
+  if (!valid) return t;
   int F[M], R[M], B[M];
 #pragma unroll
   for (int j = 0; j < M; j++) {
@@ -218,18 +260,43 @@ __device__ __forceinline__ int lb1_compute_tile(Lb1Smem& sm, const uint8_t* in_t
       load_row<M>(tab, prmu[i + 1], r1);
       int f0 = add_fma(F[0], r0[0]);
       int f1 = add_fma(f0, r1[0]);
-      R[0] = add_fma(R[0], -add_fma(r0[0], r1[0]));
+      R[0] = R[0] - r0[0] - r1[0];  // one three-input add (the kernel is issue-bound, not ALU-pipe-bound)
       F[0] = f1;
 #pragma unroll
       for (int j = 1; j < M; j++) {
         f0 = add_fma(max(f0, F[j]), r0[j]);  // job i on machine j
         f1 = add_fma(max(f1, f0), r1[j]);    // job i+1 on machine j
-        R[j] = add_fma(R[j], -add_fma(r0[j], r1[j]));
+        R[j] = R[j] - r0[j] - r1[j];
         F[j] = f1;
       }
     } else {
       schedule_job<M>(tab, prmu[i], F, R);
     }
+  }
+  if constexpr (SIMD) {
+    uint32_t F2[M], RB2[M];
+#pragma unroll
+    for (int j = 0; j < M; j++) {
+      F2[j] = static_cast<uint32_t>(F[j]) * 0x10001u;
+      RB2[j] = static_cast<uint32_t>(R[j] + B[j]) * 0x10001u;
+    }
+    // children in groups of four slots = two pairs; a pair with no live slot is skipped
+#pragma unroll
+    for (int g = 0; g < 5; g++) {
+      if (4 * g + 3 > limit1) {
+        int v[4] = {0, 0, 0, 0};
+        if (4 * g + 1 > limit1) {
+          const uint32_t x = child_pair_bound<M>(tab, F2, RB2, prmu[4 * g], prmu[4 * g + 1]);
+          v[0] = static_cast<int>(x & 0xFFFFu);
+          v[1] = static_cast<int>(x >> 16);
+        }
+        const uint32_t y = child_pair_bound<M>(tab, F2, RB2, prmu[4 * g + 2], prmu[4 * g + 3]);
+        v[2] = static_cast<int>(y & 0xFFFFu);
+        v[3] = static_cast<int>(y >> 16);
+        emit(t, limit1, g, v);
+      }
+    }
+    return t;
   }
   if constexpr (KIND == 0) {  // fold remain + back once per parent
 #pragma unroll
@@ -254,18 +321,18 @@ __device__ __forceinline__ int lb1_compute_tile(Lb1Smem& sm, const uint8_t* in_t
   return t;
 }
 
-template <int KIND, int M>
+template <int KIND, int M, bool SIMD>
 __global__ void __launch_bounds__(PF_THREADS) pfsp_lb1_kernel(const uint8_t* __restrict__ parents,
                                                              uint8_t* __restrict__ bounds, long long count,
                                                              const PfspLb1Tables* __restrict__ tables) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Lb1Smem& sm = *reinterpret_cast<Lb1Smem*>(smem_raw);
   stage_blob(&sm.tab, tables, sizeof(PfspLb1Tables), &sm.tab_bar);
-  run_tile_pipeline<LB1_STAGES, PF_TILE, PF_REC, PF_MAXJ * 4>(
-      sm.tiles, parents, bounds, count, [&sm](const uint8_t* in_tile, uint8_t* out_tile, int n, long long) {
+  run_tile_ring_inplace<PF_TILE, PF_REC, PF_MAXJ * 4>(
+      sm.tiles, parents, bounds, count, [&sm](uint8_t* tile, int n, long long) {
         // one 16-byte store per group of four slots (stride 80 B = odd multiple of 16 B: conflict free)
-        lb1_compute_tile<KIND, M>(sm, in_tile, 0, n, [out_tile](int t, int, int g, const int (&v)[4]) {
-          reinterpret_cast<int4*>(out_tile)[5 * t + g] = make_int4(v[0], v[1], v[2], v[3]);
+        lb1_compute_tile<KIND, M, SIMD, true>(sm, tile, 0, n, [tile](int t, int, int g, const int (&v)[4]) {
+          reinterpret_cast<int4*>(tile)[5 * t + g] = make_int4(v[0], v[1], v[2], v[3]);
         });
       });
 }

@@ -559,6 +559,7 @@ struct tsb_pfsp : Base {
   tsb::Lb2Const* lb2c = nullptr;  // packed Johnson tables, passed to the lb2 kernels by value (constant bank)
   bool attr_set[3] = {false, false, false};
   int occ[3] = {0, 0, 0};
+  bool simd16 = false;  // lb1 / lb1_d children two per register (values < 2^16, min_tails non-increasing)
   // fused expand + device-resident pool
   ExpandCtx ex;
   bool ex_attr[4] = {false, false, false, false};  // count lb1_d, lb1, lb2; build
@@ -573,9 +574,9 @@ struct tsb_pfsp : Base {
 
 namespace {
 
-template <int KIND, int M>
+template <int KIND, int M, bool SIMD>
 int launch_lb1_km(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
-  auto kernel = tsb::pfsp_lb1_kernel<KIND, M>;
+  auto kernel = tsb::pfsp_lb1_kernel<KIND, M, SIMD>;
   const size_t smem = sizeof(tsb::Lb1Smem) + 128;
   if (!h->attr_set[KIND]) {
     TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -611,9 +612,11 @@ int launch_pfsp(tsb_pfsp* h, int lb_kind, const uint8_t* in, uint8_t* out, long 
                 cudaStream_t s) {
   // bounds are int32 and `lb > best` can never hold for best >= INT32_MAX (Chapel's max(int) under --ub 0)
   const int best = best64 > INT_MAX ? INT_MAX : best64 < INT_MIN ? INT_MIN : static_cast<int>(best64);
-#define TSB_PF_DISPATCH(M)                                                          \
-  if (lb_kind == TSB_LB1) return launch_lb1_km<1, M>(h, in, out, count, s);         \
-  if (lb_kind == TSB_LB1_D) return launch_lb1_km<0, M>(h, in, out, count, s);       \
+#define TSB_PF_DISPATCH(M)                                                                                      \
+  if (lb_kind == TSB_LB1)                                                                                        \
+    return h->simd16 ? launch_lb1_km<1, M, true>(h, in, out, count, s) : launch_lb1_km<1, M, false>(h, in, out, count, s); \
+  if (lb_kind == TSB_LB1_D)                                                                                      \
+    return h->simd16 ? launch_lb1_km<0, M, true>(h, in, out, count, s) : launch_lb1_km<0, M, false>(h, in, out, count, s); \
   return launch_lb2_m<M>(h, in, out, count, best, s);
   if (h->mt == 5) { TSB_PF_DISPATCH(5) }
   if (h->mt == 10) { TSB_PF_DISPATCH(10) }
@@ -657,7 +660,7 @@ int pfsp_expand_m(tsb_pfsp* h, int lb_kind, const uint8_t* arena, const tsb::Exp
     TSB_CUDA(cudaMemsetAsync(ex.d_tile, 0, static_cast<size_t>(prm.n_tiles) * sizeof(int), s));
     k1<<<g1, tsb::PF_THREADS, smem1, s>>>(arena, prm, h->d_tab1, *h->lb2c, ex.d_cmask, ex.d_tile, ex.d_st);
   } else if (lb_kind == TSB_LB1) {
-    auto k1 = tsb::pfsp_expand_count_lb1_kernel<1, M>;
+    auto k1 = h->simd16 ? tsb::pfsp_expand_count_lb1_kernel<1, M, true> : tsb::pfsp_expand_count_lb1_kernel<1, M, false>;
     const size_t smem1 = sizeof(tsb::Lb1CountSmem) + 128;
     if (!h->ex_attr[1]) {
       TSB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
@@ -667,7 +670,7 @@ int pfsp_expand_m(tsb_pfsp* h, int lb_kind, const uint8_t* arena, const tsb::Exp
     if (rc != TSB_OK) return rc;
     k1<<<g1, tsb::PF_THREADS, smem1, s>>>(arena, prm, h->d_tab1, ex.d_cmask, ex.d_tile, ex.d_st);
   } else {
-    auto k1 = tsb::pfsp_expand_count_lb1_kernel<0, M>;
+    auto k1 = h->simd16 ? tsb::pfsp_expand_count_lb1_kernel<0, M, true> : tsb::pfsp_expand_count_lb1_kernel<0, M, false>;
     const size_t smem1 = sizeof(tsb::Lb1CountSmem) + 128;
     if (!h->ex_attr[0]) {
       TSB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
@@ -1032,14 +1035,27 @@ int tsb_pfsp_create(tsb_pfsp** out, int device, int jobs, int machines, int M_ma
   t1.machines = machines;
   t1.pairs = nb_pairs;
   t1.mp = mp;
+  long long sum_all = 0, max_head = 0, max_tail = 0;
+  bool nonneg = true, tails_monotone = true;
+  const int hs = tsb::half_stride(h->mt);
   for (int k = 0; k < machines; k++) {
     t1.min_heads[k] = min_heads[k];
     t1.min_tails[k] = min_tails[k];
+    max_head = std::max<long long>(max_head, min_heads[k]);
+    max_tail = std::max<long long>(max_tail, min_tails[k]);
+    nonneg &= min_heads[k] >= 0 && min_tails[k] >= 0;
+    if (k > 0) tails_monotone &= min_tails[k] <= min_tails[k - 1];
     for (int j = 0; j < jobs; j++) {
-      t1.total[k] += p_times[k * jobs + j];
-      t1.pj[j * mp + k] = p_times[k * jobs + j];
+      const int32_t pv = p_times[k * jobs + j];
+      t1.total[k] += pv;
+      t1.pj[j * mp + k] = pv;
+      nonneg &= pv >= 0;
+      sum_all += pv;
+      t1.ph[j * hs + (k >> 1)] |= static_cast<uint32_t>(pv & 0xFFFF) << (16 * (k & 1));
     }
   }
+  // every intermediate of the bounds is <= sum of all processing times + largest head + largest tail
+  h->simd16 = nonneg && tails_monotone && sum_all + max_head + max_tail < 65536 && !std::getenv("TSB200_NO_SIMD16");
   // lb2: packed Johnson tables in machine_pair_order (tsb::Lb2Const); value ranges checked, indices checked
   bool bad = false, wide = false;
   if (nb_pairs > 0) {

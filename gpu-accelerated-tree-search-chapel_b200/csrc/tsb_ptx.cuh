@@ -187,4 +187,81 @@ __device__ __forceinline__ void run_tile_pipeline(Smem& sm, const uint8_t* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// In-place variant for kernels whose output record is not larger than the input record: a ring of
+// three tile buffers, each first the TMA destination of an input tile and then — after the
+// functor has pulled its inputs into registers and synchronised — the TMA source of that tile's
+// output.  At the end of iteration i the store of tile i is issued from buffer i%3 and, once the
+// store of tile i-1 has drained its shared-memory reads (it had a whole tile time to do so), the
+// load of tile i+2 goes into buffer (i-1)%3: loads stay two tiles ahead at the shared-memory
+// cost of three input tiles and no output tiles.
+// Functor: compute(uint8_t* tile /* in and out */, int records_in_tile, long long tile_index);
+// it MUST __syncthreads() between its last read of the input and its first write of the output.
+// ---------------------------------------------------------------------------------------------
+template <int IN_BYTES>
+struct RingSmem {
+  alignas(128) uint8_t buf[3][IN_BYTES];
+  alignas(8) uint64_t full[3];
+};
+
+template <int TILE, int IN_REC, int OUT_REC, typename Smem, typename F>
+__device__ __forceinline__ void run_tile_ring_inplace(Smem& sm, const uint8_t* __restrict__ in_g,
+                                                      uint8_t* __restrict__ out_g, long long count, F&& compute) {
+  constexpr uint32_t IN_BYTES = TILE * IN_REC;
+  constexpr uint32_t OUT_BYTES = TILE * OUT_REC;
+  static_assert(IN_BYTES % 16 == 0 && OUT_BYTES % 16 == 0 && OUT_BYTES <= IN_BYTES, "tile sizes");
+  const long long full_tiles = count / TILE;
+  const int rem = static_cast<int>(count - full_tiles * TILE);
+  const int tid = threadIdx.x;
+  const long long first = blockIdx.x, stride = gridDim.x;
+  const long long my_tiles = first < full_tiles ? (full_tiles - first + stride - 1) / stride : 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < 3; s++) mbar_init(&sm.full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  uint64_t pol = 0;
+  if (tid == 0) {
+    pol = policy_evict_first();
+    for (int s = 0; s < 2 && s < my_tiles; s++) {
+      mbar_arrive_expect_tx(&sm.full[s], IN_BYTES);
+      bulk_g2s_stream(sm.buf[s], in_g + (first + s * stride) * IN_BYTES, IN_BYTES, &sm.full[s], pol);
+    }
+  }
+  for (long long it = 0; it < my_tiles; it++) {
+    const int s = static_cast<int>(it % 3);
+    const long long tile = first + it * stride;
+    mbar_wait(&sm.full[s], static_cast<uint32_t>((it / 3) & 1));
+    compute(sm.buf[s], TILE, tile);
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(out_g + tile * OUT_BYTES, sm.buf[s], OUT_BYTES);
+      bulk_commit();
+      const long long nxt = it + 2;
+      if (nxt < my_tiles) {
+        bulk_wait_read<1>();  // the store of tile it-1 (buffer nxt % 3) has drained
+        const int ns = static_cast<int>(nxt % 3);
+        mbar_arrive_expect_tx(&sm.full[ns], IN_BYTES);
+        bulk_g2s_stream(sm.buf[ns], in_g + (first + nxt * stride) * IN_BYTES, IN_BYTES, &sm.full[ns], pol);
+      }
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+  // partial last tile: owned by the CTA that would own tile index `full_tiles`
+  if (rem > 0 && (full_tiles % stride) == first) {
+    __syncthreads();
+    const uint8_t* src = in_g + full_tiles * IN_BYTES;
+    uint8_t* dst = out_g + full_tiles * OUT_BYTES;
+    uint8_t* b = sm.buf[0];
+    const int in_b = rem * IN_REC, out_b = rem * OUT_REC;
+    for (int i = tid; i < static_cast<int>(IN_BYTES); i += blockDim.x) b[i] = i < in_b ? src[i] : 0;
+    __syncthreads();
+    compute(b, rem, full_tiles);
+    __syncthreads();
+    for (int i = tid; i < out_b; i += blockDim.x) dst[i] = b[i];
+  }
+}
+
 }  // namespace tsb

@@ -195,6 +195,35 @@ def test_pfsp_random_nodes(inst, lb):
                 check_pfsp(ev, parents, lb, best - 200)   # aggressive early exit
 
 
+@pytest.mark.parametrize("inst", [14, 21])
+@pytest.mark.parametrize("lb", ["lb1", "lb1_d"])
+def test_pfsp_scalar_children_formulation(inst, lb, monkeypatch):
+    """TSB200_NO_SIMD16 selects the one-child-per-register formulation (the route for tables whose values do not
+    fit 16 bits or whose min_tails is not non-increasing); both routes must give the oracle's bounds"""
+    monkeypatch.setenv("TSB200_NO_SIMD16", "1")
+    rng = np.random.default_rng(inst)
+    with tsb200.PfspEvaluator(inst, M=6000) as ev:
+        parents = rand_pfsp(rng, ev.jobs, 6000)
+        parents["depth"][:50] = 0
+        parents["limit1"][:50] = -1
+        check_pfsp(ev, parents, lb, 10**9)
+
+
+def test_pfsp_custom_tables_with_rising_tails():
+    """min_tails that is NOT non-increasing (not what fill_min_heads_tails produces, but the C ABI takes arbitrary
+    arrays): lb1 and lb1_d then differ in value, and each must match its own oracle function"""
+    t = tsb200.taillard_tables(14)
+    for k in range(t.machines):
+        t.min_tails[k] = 40 + 37 * ((k * 7) % 5)
+    rng = np.random.default_rng(3)
+    with tsb200.PfspEvaluator(tables=t, M=4000) as ev:
+        parents = rand_pfsp(rng, 20, 4000)
+        a = check_pfsp(ev, parents, "lb1", 10**9)
+        b = check_pfsp(ev, parents, "lb1_d", 10**9)
+        live = po.pfsp_live_mask(parents.view(po.PFSP_NODE_DTYPE), 20)
+        assert (a[live] != b[live]).any()
+
+
 @pytest.mark.parametrize("inst", [1, 14, 20, 21])
 def test_pfsp_golden_vectors_from_reference(golden_dir, inst):
     gold = np.load(os.path.join(golden_dir, "pfsp_bounds.npz"))
