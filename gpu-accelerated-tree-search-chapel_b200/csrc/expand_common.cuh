@@ -99,6 +99,7 @@ __device__ __forceinline__ uint32_t tile_load_bytes(long long abs_tile, long lon
 constexpr int EXP_MAX_OWN = 256;  // tiles per CTA (host-checked)
 struct ScanSmem {
   int own[EXP_MAX_OWN];  // offset of own tile i (= tile first + i*stride)
+  int cnt[EXP_MAX_OWN];  // its child count
   int excl[256];         // children of all tiles before thread t's block of tile counts
   int part[32];
   long long total;
@@ -139,6 +140,7 @@ __device__ __forceinline__ void expand_own_offsets(ScanSmem& sc, const int* __re
 #pragma unroll 16
     for (int x = blk * per; x < j; x++) off += __ldg(&tile_sums[x]);
     sc.own[i] = off;
+    sc.cnt[i] = __ldg(&tile_sums[j]);
   }
   __syncthreads();
 }

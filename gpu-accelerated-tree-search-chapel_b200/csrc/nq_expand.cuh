@@ -8,16 +8,18 @@
 //
 // Three kernels per chunk (expand_common.cuh), the chunk read in place from the pool arena:
 //   nq_expand_count : the evaluator of nq_kernel.cuh (TMA-pipelined tiles of 512 parents), but instead of N
-//                     label bytes per parent it writes one 32-bit child mask (bit j <=> child j exists) and
-//                     one child count per tile; parents with depth == N are counted as solutions
+//                     label bytes per parent it writes the tile's ITEMS — one uint16 (parent << 5 | slot) per
+//                     child, in child order (block scan of the per-parent counts) — and one child count per
+//                     tile; parents with depth == N are counted as solutions
 //   nq_expand_build : tile counts -> offsets of the CTA's own tiles (prologue); per tile (2-stage TMA prefetch
-//                     of parents + masks): block scan of the per-parent counts, children built in shared
+//                     of parents + items, no scan left to do): children built in shared
 //                     memory as a contiguous byte image at the 16-byte phase of their destination — one thread
 //                     per child, the parent read as six aligned words, the two queens swapped by an XOR patch
 //                     in registers, realigned by funnel shifts and stored as words (+ the few bytes of the two
 //                     words it shares with its neighbours) — and written with one TMA bulk store plus < 16
 //                     head / tail bytes (21-byte records land at any alignment)
-// HBM traffic per parent: 21 B + 4 B (count) and 21 B (mostly L2) + 4 B + 21 B per child (build).
+// HBM traffic per parent: 21 B (count) + 2 B per child (items, written and re-read) and 21 B (mostly L2) + 21 B per
+// child (build).
 #pragma once
 #include "expand_common.cuh"
 #include "nq_kernel.cuh"
@@ -103,10 +105,11 @@ struct NqCountSmem {
   int warp_tot[4];
 };
 
+// items of a tile: one uint16 per child, (record << 5) | slot, in child order, at items[lin * NQ_TILE * N ...]
 template <int N>
 __global__ void __launch_bounds__(NQ_THREADS) nq_expand_count_kernel(const uint8_t* __restrict__ arena,
                                                                     const __grid_constant__ ExpandParams prm,
-                                                                    uint32_t* __restrict__ cmask,
+                                                                    uint16_t* __restrict__ items,
                                                                     int* __restrict__ tile_sums,
                                                                     ExpandState* __restrict__ st) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -141,18 +144,36 @@ __global__ void __launch_bounds__(NQ_THREADS) nq_expand_count_kernel(const uint8
     uint32_t cm[4];
     int leaves;
     nq_eval_quad<N>(sm.in[s], at * NQ_TILE, lo, hi, cm, leaves);
-    reinterpret_cast<uint4*>(cmask)[static_cast<long long>(lin) * (NQ_TILE / 4) + t] =
-        make_uint4(cm[0], cm[1], cm[2], cm[3]);
-    int packed = (__popc(cm[0]) + __popc(cm[1]) + __popc(cm[2]) + __popc(cm[3])) | (leaves << 20);
+    // block scan of the child counts (leaves ride in the upper bits)
+    const int mine = __popc(cm[0]) + __popc(cm[1]) + __popc(cm[2]) + __popc(cm[3]);
+    int incl = mine | (leaves << 20);  // children of a tile <= 512*20 < 2^20
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
-    if (lane == 0) sm.warp_tot[wid] = packed;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) sm.warp_tot[wid] = incl;
     __syncthreads();  // everyone is done with in[s]; warp totals visible
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (i < wid) woff += sm.warp_tot[i];
+      tot += sm.warp_tot[i];
+    }
     if (t == 0) {
-      const int tot = sm.warp_tot[0] + sm.warp_tot[1] + sm.warp_tot[2] + sm.warp_tot[3];
-      tile_sums[lin] = tot & 0xFFFFF;  // children of a tile <= 512*20 < 2^20
+      tile_sums[lin] = tot & 0xFFFFF;
       my_solutions += static_cast<unsigned>(tot >> 20);
       if (lin + 2 * stride < prm.n_tiles) issue(lin + 2 * stride, s);
+    }
+    uint16_t* gi = items + static_cast<long long>(lin) * (NQ_TILE * N) + (((woff + incl) & 0xFFFFF) - mine);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      uint32_t m = cm[q];
+      while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        *gi++ = static_cast<uint16_t>(((4 * t + q) << 5) | k);
+      }
     }
     __syncthreads();  // warp_tot free for the next tile
   }
@@ -162,11 +183,10 @@ __global__ void __launch_bounds__(NQ_THREADS) nq_expand_count_kernel(const uint8
 // ------------------------------------------------------------------------------------------- build
 struct NqBuildSmem {
   alignas(128) uint8_t in[2][NQ_TILE * NQ_REC];
-  alignas(128) uint32_t mask[2][NQ_TILE];
+  alignas(128) uint16_t item[2][EXP_CAP];  // first window of the tile's items
   alignas(128) uint8_t stage[EXP_CAP * NQ_REC + 32];
-  alignas(8) uint64_t full[2];
-  uint16_t item[EXP_CAP];  // (record << 5) | slot, in child order
-  int warp_tot[4];
+  alignas(8) uint64_t full[2];             // two arrivals per phase: parents, items
+  alignas(8) uint64_t wbar;                // further item windows of dense tiles
   ScanSmem scan;
 };
 
@@ -265,91 +285,80 @@ __device__ __forceinline__ void nq_build_child_warp(const uint8_t* in_tile, int 
 template <int N>
 __global__ void __launch_bounds__(NQ_THREADS) nq_expand_build_kernel(const uint8_t* __restrict__ arena,
                                                                     const __grid_constant__ ExpandParams prm,
-                                                                    const uint32_t* __restrict__ cmask,
+                                                                    const uint16_t* __restrict__ items,
                                                                     const int* __restrict__ tile_sums,
                                                                     uint8_t* __restrict__ children,
                                                                     ExpandState* __restrict__ st,
                                                                     ExpandResult* __restrict__ res) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   NqBuildSmem& sm = *reinterpret_cast<NqBuildSmem*>(smem_raw);
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int t = threadIdx.x;
   constexpr uint32_t IN_BYTES = NQ_TILE * NQ_REC;
+  constexpr long long IST = static_cast<long long>(NQ_TILE) * N;  // items per tile slot
   const int first = blockIdx.x, stride = gridDim.x;
   if (t == 0) {
-    mbar_init(&sm.full[0], 1);
-    mbar_init(&sm.full[1], 1);
+    mbar_init(&sm.full[0], 2);
+    mbar_init(&sm.full[1], 2);
+    mbar_init(&sm.wbar, 1);
     mbar_fence_init();
   }
   __syncthreads();
   uint64_t pol = 0;
   if (t == 0) pol = policy_evict_first();
-  auto issue = [&](int lin, int s) {  // thread 0: parents + masks of one tile
+  auto issue_parents = [&](int lin, int s) {  // thread 0
     long long at, lo, hi;
     piece_of(prm, lin, NQ_TILE, at, lo, hi);
     const uint32_t nb = tile_load_bytes(at, hi, NQ_TILE, NQ_REC);
-    mbar_arrive_expect_tx(&sm.full[s], nb + NQ_TILE * 4);
+    mbar_arrive_expect_tx(&sm.full[s], nb);
     bulk_g2s_stream(sm.in[s], arena + at * IN_BYTES, nb, &sm.full[s], pol);
-    bulk_g2s_stream(sm.mask[s], cmask + static_cast<long long>(lin) * NQ_TILE, NQ_TILE * 4, &sm.full[s], pol);
   };
-  if (t == 0) {
-    if (first < prm.n_tiles) issue(first, 0);
-    if (first + stride < prm.n_tiles) issue(first + stride, 1);
+  auto issue_items = [&](int lin, int s, int cnt) {  // thread 0: the first window of the tile's items
+    const uint32_t nb = (static_cast<uint32_t>(min(cnt, EXP_CAP)) * 2u + 15u) & ~15u;
+    mbar_arrive_expect_tx(&sm.full[s], nb);
+    if (nb) bulk_g2s_stream(sm.item[s], items + lin * IST, nb, &sm.full[s], pol);
+  };
+  if (t == 0) {  // the parents of the first two tiles are on their way while the offsets are computed
+    if (first < prm.n_tiles) issue_parents(first, 0);
+    if (first + stride < prm.n_tiles) issue_parents(first + stride, 1);
   }
   expand_own_offsets<NQ_THREADS>(sm.scan, tile_sums, prm.n_tiles, first, stride);
   expand_publish(sm.scan, st, res, prm.epoch, 0);
-  unsigned it = 0;
+  if (t == 0) {
+    if (first < prm.n_tiles) issue_items(first, 0, sm.scan.cnt[0]);
+    if (first + stride < prm.n_tiles) issue_items(first + stride, 1, sm.scan.cnt[1]);
+  }
+  unsigned it = 0, wphase = 0;
   for (int lin = first; lin < prm.n_tiles; lin += stride, it++) {
     const int s = it & 1;
-    mbar_wait(&sm.full[s], (it >> 1) & 1u);
-    const uint4 cmv = reinterpret_cast<const uint4*>(sm.mask[s])[t];
-    const uint32_t cm[4] = {cmv.x, cmv.y, cmv.z, cmv.w};
-    const int mine = __popc(cm[0]) + __popc(cm[1]) + __popc(cm[2]) + __popc(cm[3]);
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    if (lane == 31) sm.warp_tot[wid] = incl;
-    if (t == 0) bulk_wait_read<0>();  // the previous tile's bulk store has drained the staging image
-    __syncthreads();  // (A)
-    int woff = 0, total = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (i < wid) woff += sm.warp_tot[i];
-      total += sm.warp_tot[i];
-    }
-    const int pos0 = woff + incl - mine;  // index (within the tile) of this thread's first child
+    const int total = sm.scan.cnt[it];
     uint8_t* const gtile = children + static_cast<long long>(sm.scan.own[it]) * NQ_REC;
+    mbar_wait(&sm.full[s], (it >> 1) & 1u);
     for (int c0 = 0; c0 < total; c0 += EXP_CAP) {  // windows of EXP_CAP children (one, except for dense tiles)
       const int cnt = min(EXP_CAP, total - c0);
-      if (c0 > 0 && t == 0) bulk_wait_read<0>();  // the previous window's bulk store has drained the image
-      int pos = pos0 - c0;
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        uint32_t m = cm[q];
-        while (m) {
-          const int k = __ffs(m) - 1;
-          m &= m - 1;
-          if (pos >= 0 && pos < EXP_CAP) sm.item[pos] = static_cast<uint16_t>(((4 * t + q) << 5) | k);
-          pos++;
+      if (c0 > 0) {  // dense tile: fetch the next window of items (everyone passed (B) of the previous window)
+        if (t == 0) {
+          const uint32_t nb = (static_cast<uint32_t>(cnt) * 2u + 15u) & ~15u;
+          mbar_arrive_expect_tx(&sm.wbar, nb);
+          bulk_g2s_stream(sm.item[s], items + lin * IST + c0, nb, &sm.wbar, pol);
         }
+        mbar_wait(&sm.wbar, wphase);
+        wphase ^= 1u;
       }
-      __syncthreads();  // (B) items
-      // one thread per child
+      if (t == 0) bulk_wait_read<0>();  // the previous bulk store has drained the staging image
+      __syncthreads();  // (A)
       uint8_t* gdst = gtile + static_cast<long long>(c0) * NQ_REC;
       const int phase = static_cast<int>(reinterpret_cast<uintptr_t>(gdst) & 15);  // image and destination share it
       uint8_t* sdst = sm.stage + phase;
       // the first (-phase) & 3 children byte-wise, so that the warps' runs of 32 children start on a word
       const int c_head = min(cnt, (4 - (phase & 3)) & 3);
-      if (t < c_head) nq_build_child(sm.in[s], sm.item[t], sm.stage, phase + t * NQ_REC);
+      if (t < c_head) nq_build_child(sm.in[s], sm.item[s][t], sm.stage, phase + t * NQ_REC);
       for (int cb = c_head; cb < cnt; cb += NQ_THREADS) {
         const int c = cb + t;
         const bool active = c < cnt;
-        nq_build_child_warp(sm.in[s], active ? sm.item[c] : 0, sm.stage, phase + c * NQ_REC, active);
+        nq_build_child_warp(sm.in[s], active ? sm.item[s][c] : 0, sm.stage, phase + c * NQ_REC, active);
       }
       fence_async_smem();
-      __syncthreads();  // (C) image complete; item free
+      __syncthreads();  // (B) image complete; in[s] / item[s] free after the last window
       const int bytes = cnt * NQ_REC;
       const int head = min(bytes, static_cast<int>((16 - (reinterpret_cast<uintptr_t>(gdst) & 15)) & 15));
       const int mid = (bytes - head) & ~15;
@@ -360,12 +369,16 @@ __global__ void __launch_bounds__(NQ_THREADS) nq_expand_build_kernel(const uint8
         bulk_s2g(gdst + head, sdst + head, static_cast<uint32_t>(mid));
         bulk_commit();
       }
-      // the head / tail bytes are read from the image after (C) by threads 1..47, which reach the next (B)
+      // the head / tail bytes are read from the image after (B) by threads 1..47, which reach the next (A)
       // — after which the image is rewritten — only when they are done
     }
-    // in[s] and mask[s] are free: every thread passed (A) after reading its masks and, if the tile had
-    // children, (C) after reading the parents
-    if (t == 0 && lin + 2 * stride < prm.n_tiles) issue(lin + 2 * stride, s);
+    // a tile without children has no barrier of its own: without this one thread 0 could re-arm full[s] twice
+    // (tiles it+2, it+4) before a slow warp has tested the phase of tile it
+    if (total == 0) __syncthreads();
+    if (t == 0 && lin + 2 * stride < prm.n_tiles) {
+      issue_parents(lin + 2 * stride, s);
+      issue_items(lin + 2 * stride, s, sm.scan.cnt[it + 2]);
+    }
   }
   if (t == 0) bulk_wait_all();
 }

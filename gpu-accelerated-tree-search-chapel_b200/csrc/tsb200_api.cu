@@ -280,10 +280,11 @@ struct PoolExtent {
 
 // state of the fused expand kernels of one handle (expand_common.cuh)
 struct ExpandCtx {
-  uint32_t* d_cmask = nullptr;  // one child mask per parent of the round (tile-linear order)
-  int* d_tile = nullptr;        // per-tile child counts, then offsets
+  uint32_t* d_cmask = nullptr;  // side array of the round, `side_bytes` per tile: PFSP: one child mask per parent;
+                                // N-Queens: the tile's items (one uint16 per child)
+  int* d_tile = nullptr;        // per-tile child counts
   long long tile_cap = 0;       // tiles the two arrays above hold
-  int tile_records = 0;
+  long long side_bytes = 0;
   tsb::ExpandState* d_st = nullptr;
   tsb::ExpandResult* h_res = nullptr;  // pinned + mapped: written by the scan kernel of a round
   tsb::ExpandResult* d_res = nullptr;  // device alias of h_res
@@ -292,7 +293,7 @@ struct ExpandCtx {
   bool attr_set = false;
   // (clears are ordered on the stream the kernels run on: the handle's streams do not synchronise with the
   // legacy default stream)
-  int reserve(long long tiles, int records_per_tile, cudaStream_t s, int best_init = 0x7FFFFFFF) {
+  int reserve(long long tiles, long long side_bytes_per_tile, cudaStream_t s, int best_init = 0x7FFFFFFF) {
     if (!d_st) {
       TSB_CUDA(cudaMalloc(&d_st, sizeof(tsb::ExpandState)));
       const tsb::ExpandState init{0ull, best_init, 0};
@@ -303,17 +304,17 @@ struct ExpandCtx {
       TSB_CUDA(cudaHostAlloc(&h_res, sizeof(tsb::ExpandResult), cudaHostAllocPortable | cudaHostAllocMapped));
       TSB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_res), h_res, 0));
     }
-    if (tiles > tile_cap || records_per_tile != tile_records) {
+    if (tiles > tile_cap || side_bytes_per_tile != side_bytes) {
       if (d_cmask) cudaFree(d_cmask);
       if (d_tile) cudaFree(d_tile);
       d_cmask = nullptr;
       d_tile = nullptr;
       tile_cap = 0;
       const long long cap = std::max<long long>(tiles + tiles / 4 + 16, 1024);
-      TSB_CUDA(cudaMalloc(&d_cmask, static_cast<size_t>(cap) * records_per_tile * 4));
+      TSB_CUDA(cudaMalloc(&d_cmask, static_cast<size_t>(cap) * side_bytes_per_tile + 64));
       TSB_CUDA(cudaMalloc(&d_tile, static_cast<size_t>(cap) * sizeof(int)));
       tile_cap = cap;
-      tile_records = records_per_tile;
+      side_bytes = side_bytes_per_tile;
     }
     return TSB_OK;
   }
@@ -480,7 +481,9 @@ int nq_expand_n(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& 
   int rc = make_params(pieces, tsb::NQ_TILE, &prm);
   if (rc != TSB_OK) return rc;
   ExpandCtx& ex = h->ex;
-  rc = ex.reserve(prm.n_tiles, tsb::NQ_TILE, s);
+  // (sized for the largest round up front: the items array is 1 KB * N per tile)
+  rc = ex.reserve(std::max<long long>(prm.n_tiles, h->M_max / tsb::NQ_TILE + 2 * tsb::EXP_MAX_PIECES),
+                  static_cast<long long>(tsb::NQ_TILE) * N * 2, s);
   if (rc != TSB_OK) return rc;
   auto k1 = tsb::nq_expand_count_kernel<N>;
   auto k3 = tsb::nq_expand_build_kernel<N>;
@@ -498,8 +501,9 @@ int nq_expand_n(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& 
   if (rc != TSB_OK) return rc;
   prm.epoch = ++ex.epoch;
   if ((prm.n_tiles + g3 - 1) / g3 > tsb::EXP_MAX_OWN) return TSB_EINVAL;  // (M_max * N < 2^31 keeps this far away)
-  k1<<<g1, tsb::NQ_THREADS, smem1, s>>>(arena, prm, ex.d_cmask, ex.d_tile, ex.d_st);
-  k3<<<g3, tsb::NQ_THREADS, smem3, s>>>(arena, prm, ex.d_cmask, ex.d_tile, children_d, ex.d_st, ex.d_res);
+  uint16_t* d_items = reinterpret_cast<uint16_t*>(ex.d_cmask);
+  k1<<<g1, tsb::NQ_THREADS, smem1, s>>>(arena, prm, d_items, ex.d_tile, ex.d_st);
+  k3<<<g3, tsb::NQ_THREADS, smem3, s>>>(arena, prm, d_items, ex.d_tile, children_d, ex.d_st, ex.d_res);
   TSB_CUDA(cudaGetLastError());
   h->launches += 2;
   TSB_CUDA(cudaStreamSynchronize(s));
@@ -718,7 +722,7 @@ int pfsp_expand_round(tsb_pfsp* h, int lb_kind, const uint8_t* arena, const std:
   if (rc != TSB_OK) return rc;
   const int best_launch = clamp_best(*best);
   ExpandCtx& ex = h->ex;
-  rc = ex.reserve(prm.n_tiles, tsb::PF_TILE, s);
+  rc = ex.reserve(std::max<long long>(prm.n_tiles, h->M_max / tsb::PF_TILE + 2 * tsb::EXP_MAX_PIECES), tsb::PF_TILE * 4, s);
   if (rc != TSB_OK) return rc;
   prm.epoch = ++ex.epoch;
   prm.best = best_launch;
