@@ -468,7 +468,9 @@ def main():
         threads = os.cpu_count() or 1
         P = min(args.M, 1 << 21)
         sample = synth_nq_parents(N, P, 1234, tsb200.NQ_NODE_DTYPE)
-        rep = max(1, int(2.0 * 12e6 * threads / P))  # ~2 s per step on this host
+        # bounded: the whole run (warm-up + steps) is sized for about one minute of wall time on this host
+        per_step_s = min(2.0, 60.0 / (args.steps + args.warmup))
+        rep = max(1, int(per_step_s * 1.3e6 * threads / P))  # ~1.3 M parents/s/thread for the reference's isSafe loop
         for _ in range(args.warmup):
             cpu_eval("nq", sample, threads, repeat=1)
         t, src = 0.0, "port"
@@ -486,7 +488,7 @@ def main():
         if not args.no_pfsp:
             Pp = 1 << 17
             ps = synth_pfsp_parents(Pp, 99, tsb200.PFSP_NODE_DTYPE)
-            dt, src2 = cpu_eval("pfsp", ps, threads, repeat=max(1, int(3.0 * 0.7e6 * threads / Pp)))
+            dt, src2 = cpu_eval("pfsp", ps, threads, repeat=max(1, int(3.0 * 0.08e6 * threads / Pp)))
             line["pfsp"] = {"workload": "PFSP ta014 lb1 ub=1", "value": Pp / dt / 1e6, "unit": "Mnodes/s",
                             "cores": threads, "kind": src2, "sample": f"{Pp} parents"}
         emit(line)
