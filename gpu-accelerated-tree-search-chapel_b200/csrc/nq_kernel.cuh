@@ -100,6 +100,16 @@ struct NqParent {
     U = 0;
     fill_amt<0>(w);
   }
+  // VAR 2: every byte by its own LDS.U8 (thread stride 84 B = 21 words: conflict free) instead of word loads +
+  // shifts — the shifts run on the ALU pipe, which is this kernel's limiter; the LSU pipe is idle
+  __device__ __forceinline__ void init_bytes(const uint8_t* pb) {
+    depth = pb[21 * Q];
+    ph = shl_clamp(1u, depth - 1u);
+    rb = shl_clamp(1u, 32u - depth);
+    U = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) amt[i] = pb[21 * Q + 1 + i];
+  }
   template <int I>
   __device__ __forceinline__ void fill_amt(const uint32_t* w) {
     if constexpr (I < N) {
@@ -144,9 +154,6 @@ template <int N, int VAR>
 __device__ __forceinline__ void nq_compute_tile(const uint8_t* in_tile, uint8_t* out_tile, int /*records*/) {
   const uint32_t* in_w = reinterpret_cast<const uint32_t*>(in_tile) + 21 * threadIdx.x;
   uint32_t* out_w = reinterpret_cast<uint32_t*>(out_tile) + N * threadIdx.x;
-  uint32_t w[21];
-#pragma unroll
-  for (int i = 0; i < 21; i++) w[i] = in_w[i];
   uint32_t o[N];
 #pragma unroll
   for (int i = 0; i < N; i++) o[i] = 0;
@@ -155,10 +162,21 @@ __device__ __forceinline__ void nq_compute_tile(const uint8_t* in_tile, uint8_t*
   NqParent<N, 1, VAR> p1;
   NqParent<N, 2, VAR> p2;
   NqParent<N, 3, VAR> p3;
-  p0.init(w);
-  p1.init(w);
-  p2.init(w);
-  p3.init(w);
+  if constexpr (VAR == 2) {
+    const uint8_t* pb = in_tile + 84 * threadIdx.x;
+    p0.init_bytes(pb);
+    p1.init_bytes(pb);
+    p2.init_bytes(pb);
+    p3.init_bytes(pb);
+  } else {
+    uint32_t w[21];
+#pragma unroll
+    for (int i = 0; i < 21; i++) w[i] = in_w[i];
+    p0.init(w);
+    p1.init(w);
+    p2.init(w);
+    p3.init(w);
+  }
   const uint32_t dmax = max(max(p0.depth, p1.depth), max(p2.depth, p3.depth));
   const uint32_t dmin = min(min(p0.depth, p1.depth), min(p2.depth, p3.depth));
 

@@ -132,8 +132,9 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_expand_count_lb1_kernel(const
 }
 
 // ------------------------------------------------------------------------------------------- count: lb2
+template <int M>
 struct Lb2CountSmem {
-  Lb2Smem core;  // tiles.in[0..1]: two input stages
+  Lb2Smem<M> core;  // tiles.in[0..1]: two input stages
   uint32_t cmask[LB2_TILE];
   uint32_t leafs[LB2_TILE];
   int red[8];
@@ -142,17 +143,17 @@ struct Lb2CountSmem {
 // (tiles of LB2_TILE = 64 parents: two linear tiles of this kernel make one 128-parent tile of the build
 // kernel, so masks and counts are laid out for PF_TILE: mask index = lin * 64 + t, tile_sums[lin / 2] is
 // accumulated with an atomicAdd — the host clears tile_sums before the launch)
-template <int M>
+template <int M, typename CT>
 __global__ void __launch_bounds__(PF_THREADS) pfsp_expand_count_lb2_kernel(const uint8_t* __restrict__ arena,
                                                                           const __grid_constant__ ExpandParams prm,
                                                                           const PfspLb1Tables* __restrict__ tables1,
-                                                                          const __grid_constant__ Lb2Const C,
+                                                                          const __grid_constant__ CT C,
                                                                           uint32_t* __restrict__ cmask,
                                                                           int* __restrict__ tile_sums,
                                                                           ExpandState* __restrict__ st) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  Lb2CountSmem& sm = *reinterpret_cast<Lb2CountSmem*>(smem_raw);
-  stage_blob(&sm.core.tab1, tables1, sizeof(PfspLb1Tables), &sm.core.tab_bar[0]);
+  Lb2CountSmem<M>& sm = *reinterpret_cast<Lb2CountSmem<M>*>(smem_raw);
+  lb2_stage_tables(sm.core, tables1, C);
   const int jobs = sm.core.tab1.jobs, best = prm.best;
   unsigned my_solutions = 0;
   // this kernel walks the round in half tiles: linear half-tile h covers records [64h, 64h+64) of linear tile h/2

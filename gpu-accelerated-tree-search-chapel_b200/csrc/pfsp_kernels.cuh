@@ -13,6 +13,8 @@
 //     child remain  rc[j] = remain[j] - p[j][job]               (sum_unscheduled :94-106 on the child)
 // which is exact integer arithmetic, so every bound is bit-identical to the reference.
 #pragma once
+#include <type_traits>
+
 #include "tsb_ptx.cuh"
 
 namespace tsb {
@@ -364,54 +366,99 @@ struct Lb2Const {
   uint32_t jp[PF_MAXP * PF_MAXJ];
 };
 static_assert(sizeof(Lb2Const) <= 16 * 1024, "must fit the kernel parameter space next to the other arguments");
+// v3, for instances with at most 10 machines (45 pairs) whose values fit 16 bits: one table word per USE (nothing
+// is unpacked) and the Johnson recurrence of a pair (compute_cmax_johnson, Bound_johnson.chpl:188-212)
+//     t0 += p0[j];   t1 = max(t1, t0 + lag[j]) + p1[j]        over the unscheduled jobs j in Johnson order
+// rewritten in closed max-plus form.  With A_j = sum_{i<=j} p0[i], B_j = sum_{i<j} p1[i] over the unscheduled jobs,
+//     t0_final = t0 + S0,      t1_final = S1 + max(t1, t0 + max_j (A_j - B_j + lag[j]))
+// where S0, S1 = the child's remaining work on the two machines (known per child: remain - its own job).  Exact in
+// integers, and the per-position work becomes two INDEPENDENT one-instruction chains
+//     D = E + c1[j];  m = max(m, D);  E += c2[j]        c1 = p0 + lag,  c2 = p0 - p1
+// instead of one three-instruction dependent chain — the kernel is latency-bound on that chain, not issue-bound
+// (a fully unrolled pair loop with half the instructions ran no faster, and slower from 280 KB of code).
+// The constant bank turned out to be the wrong home for one-word-per-use tables (three LDC per position cost more
+// than the unpacking they save), so for <= 10 machines the table lives in SHARED memory as one uint4 per
+// (pair, position) = {1 << job, c1, c2, 0}: a single broadcast LDS.128 per position, no unpacking, four ALU-pipe
+// instructions (scheduled-bit test, add, max, add).
+constexpr int LB2U_PAIRS = 45;
+struct Lb2TabU {
+  uint4 e[LB2U_PAIRS * PF_MAXJ];  // {bit, c1 = p[ma0] + lag, c2 = p[ma0] - p[ma1], 0} in machine_pair_order / Johnson order
+  uint32_t mach[LB2U_PAIRS + 3];  // ma0 | ma1 << 8
+  uint32_t tails[LB2U_PAIRS + 3]; // min_tails[ma0] | min_tails[ma1] << 16
+};
+static_assert(sizeof(Lb2TabU) % 16 == 0, "blob must be a multiple of 16 B");
+struct Lb2ConstU {  // kernel-parameter form of the route: just the device address of the table
+  const Lb2TabU* tab;
+};
 using Lb2Tiles = TileSmem<LB2_STAGES, LB2_TILE * PF_REC, LB2_TILE * PF_MAXJ * 4>;
 
+struct Lb2TabNone {
+  uint4 e[1];
+  uint32_t mach[4], tails[4];
+};
+template <int M>
+struct Lb2TabSlot {
+  using type = typename std::conditional<(M <= 10), Lb2TabU, Lb2TabNone>::type;
+};
+template <int M>
 struct Lb2Smem {
   Lb2Tiles tiles;
   alignas(16) PfspLb1Tables tab1;
   alignas(8) uint64_t tab_bar[2];
-  int32_t front[PF_MAXM][LB2_TILE];             // parent fronts, [machine][parent]
-  int32_t fc[PF_MAXM][PF_THREADS];              // per-thread child front scratch, [machine][thread]
+  int32_t front[M][LB2_TILE];                   // parent fronts, [machine][parent]
+  int32_t remain[M][LB2_TILE];                  // parent remaining work, [machine][parent]
+  int32_t fc[M][PF_THREADS];                    // per-thread child front scratch, [machine][thread]
+  int32_t rc[M][PF_THREADS];                    // per-thread child remaining work
+  alignas(16) typename Lb2TabSlot<M>::type tabu;  // the Lb2ConstU route's table (M <= 10 only)
   uint32_t sched[LB2_TILE];                     // bit j set <=> job j scheduled in the parent
   uint32_t list[2][LB2_TILE * PF_MAXJ];         // active children: parent << 24 | slot << 16 | running lb
   int32_t n_list[2];
 };
 
-// `emit(p, k, lb)` receives the bound of every live (parent p, slot k) of the tile's parents [rec_lo, rec_hi);
-// `dead(p, k)` is called for the slots below the live range (the evaluator zeroes them).
-template <int M, typename Emit, typename Dead>
-__device__ __forceinline__ void lb2_compute_tile(Lb2Smem& sm, const Lb2Const& C, const uint8_t* in_tile, int rec_lo,
-                                                 int rec_hi, int best, Emit&& emit, Dead&& dead) {
+// child front = add_forward(parent front, job) into this thread's column of sm.fc; returns the scheduled mask
+template <int M>
+__device__ __forceinline__ uint32_t lb2_child_front(Lb2Smem<M>& sm, const int32_t* nodes, int p, int k) {
   const int t = threadIdx.x;
   const PfspLb1Tables& tab = sm.tab1;
-  const int jobs = tab.jobs;
-  const int32_t* nodes = reinterpret_cast<const int32_t*>(in_tile);
-
-  if (t < 2) sm.n_list[t] = 0;
-  __syncthreads();
-  // ---- phase A
-  if (t < LB2_TILE && t >= rec_lo && t < rec_hi) {
-    const int32_t* node = nodes + 22 * t;
-    const int limit1 = min(max(node[1], -1), PF_MAXJ - 1);
-    int F[M], R[M];
-    parent_front_remain<M>(tab, node, limit1, false, F, R);  // lb2 children always have limit1 >= 0
+  const int job = nodes[22 * p + 2 + k];
+  int row[M];
+  load_row<M>(tab, job, row);
+  int f = sm.front[0][p] + row[0];
+  sm.fc[0][t] = f;
+  sm.rc[0][t] = sm.remain[0][p] - row[0];
 #pragma unroll
-    for (int j = 0; j < M; j++) sm.front[j][t] = F[j];
-    uint32_t mask = 0;
-    for (int i = 0; i <= limit1; i++) mask |= 1u << node[2 + i];
-    sm.sched[t] = mask;
-    const int live = jobs - 1 - limit1;
-    int base = live > 0 ? atomicAdd(&sm.n_list[0], live) : 0;
-    for (int k = 0; k < jobs; k++) {
-      if (k > limit1)
-        sm.list[0][base++] = (static_cast<uint32_t>(t) << 24) | (static_cast<uint32_t>(k) << 16);
-      else
-        dead(t, k);
-    }
+  for (int j = 1; j < M; j++) {
+    f = max(f, sm.front[j][p]) + row[j];
+    sm.fc[j][t] = f;
+    sm.rc[j][t] = sm.remain[j][p] - row[j];
+  }
+  return sm.sched[p] | (1u << job);
+}
+
+// instance tables -> shared memory (one or two bulk copies on one barrier)
+template <int M>
+__device__ __forceinline__ void lb2_stage_tables(Lb2Smem<M>& sm, const PfspLb1Tables* tables1, const Lb2Const&) {
+  stage_blob(&sm.tab1, tables1, sizeof(PfspLb1Tables), &sm.tab_bar[0]);
+}
+template <int M>
+__device__ __forceinline__ void lb2_stage_tables(Lb2Smem<M>& sm, const PfspLb1Tables* tables1, const Lb2ConstU& C) {
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.tab_bar[0], 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&sm.tab_bar[0], sizeof(PfspLb1Tables) + (M <= 10 ? sizeof(Lb2TabU) : 0));
+    bulk_g2s(&sm.tab1, tables1, sizeof(PfspLb1Tables), &sm.tab_bar[0]);
+    if constexpr (M <= 10) bulk_g2s(&sm.tabu, C.tab, sizeof(Lb2TabU), &sm.tab_bar[0]);
   }
   __syncthreads();
-  // ---- phase B
-  const int pairs = tab.pairs;
+  mbar_wait(&sm.tab_bar[0], 0);
+}
+
+// ---- phase B, packed tables, rolled pair loop (any machine count)
+template <int M, typename Emit>
+__device__ __forceinline__ void lb2_phase_b(Lb2Smem<M>& sm, const Lb2Const& C, const int32_t* nodes, int best,
+                                            Emit&& emit) {
+  const int t = threadIdx.x;
+  const int pairs = sm.tab1.pairs;
   int cur = 0;
   for (int l0 = 0; l0 < pairs; l0 += LB2_CHUNK, cur ^= 1) {
     const int n_act = sm.n_list[cur];
@@ -422,19 +469,7 @@ __device__ __forceinline__ void lb2_compute_tile(Lb2Smem& sm, const Lb2Const& C,
       const uint32_t e = sm.list[cur][it];
       const int p = e >> 24, k = (e >> 16) & 31;
       int lb = e & 0xFFFF;
-      const int job = nodes[22 * p + 2 + k];
-      const uint32_t mask = sm.sched[p] | (1u << job);
-      {  // child front = add_forward(parent front, job)
-        int row[M];
-        load_row<M>(tab, job, row);
-        int f = sm.front[0][p] + row[0];
-        sm.fc[0][t] = f;
-#pragma unroll
-        for (int j = 1; j < M; j++) {
-          f = max(f, sm.front[j][p]) + row[j];
-          sm.fc[j][t] = f;
-        }
-      }
+      const uint32_t mask = lb2_child_front<M>(sm, nodes, p, k);
       bool over = false;
       for (int l = l0; l < l1; l++) {
         const uint32_t pi = C.pair[l];
@@ -468,14 +503,109 @@ __device__ __forceinline__ void lb2_compute_tile(Lb2Smem& sm, const Lb2Const& C,
   }
 }
 
-template <int M>
+// ---- phase B, one-word-per-use tables (Lb2ConstU): pairs rolled, the 20 positions unrolled
+// (a fully unrolled pair loop — 45 x 20 positions, every table word an immediate-address constant load — was
+// measured SLOWER than this: 280 KB of code per kernel)
+template <int M, typename Emit>
+__device__ __forceinline__ void lb2_phase_b(Lb2Smem<M>& sm, const Lb2ConstU&, const int32_t* nodes, int best,
+                                            Emit&& emit) {
+  const int t = threadIdx.x;
+  const int pairs = sm.tab1.pairs;
+  int cur = 0;
+  for (int l0 = 0; l0 < pairs; l0 += LB2_CHUNK, cur ^= 1) {
+    const int n_act = sm.n_list[cur];
+    if (n_act == 0) break;  // (uniform)
+    const int l1 = min(pairs, l0 + LB2_CHUNK);
+    const bool last = l1 == pairs;
+    for (int it = t; it < n_act; it += PF_THREADS) {
+      const uint32_t e = sm.list[cur][it];
+      const int p = e >> 24, k = (e >> 16) & 31;
+      int lb = e & 0xFFFF;
+      const uint32_t mask = lb2_child_front<M>(sm, nodes, p, k);
+      bool over = false;
+      for (int l = l0; l < l1; l++) {
+        const uint32_t mm = sm.tabu.mach[l];
+        const int ma0 = mm & 255u, ma1 = mm >> 8;
+        const uint4* te = &sm.tabu.e[l * PF_MAXJ];
+        int E = 0, m = -(1 << 28);
+#pragma unroll
+        for (int j = 0; j < PF_MAXJ; j++) {
+          const uint4 w = te[j];  // broadcast LDS.128
+          if (!(mask & w.x)) {
+            m = max(m, E + static_cast<int>(w.y));
+            E += static_cast<int>(w.z);
+          }
+        }
+        const uint32_t tl = sm.tabu.tails[l];
+        const int t0 = sm.fc[ma0][t];
+        const int t1f = sm.rc[ma1][t] + max(sm.fc[ma1][t], t0 + m);
+        const int c = max(t1f + static_cast<int>(tl >> 16), t0 + sm.rc[ma0][t] + static_cast<int>(tl & 0xFFFFu));
+        lb = max(lb, c);
+        if (lb > best) {
+          over = true;
+          break;
+        }
+      }
+      if (over || last) {
+        emit(p, k, lb);
+      } else {
+        const int at = atomicAdd(&sm.n_list[cur ^ 1], 1);
+        sm.list[cur ^ 1][at] = (e & 0xFFFF0000u) | static_cast<uint32_t>(lb);
+      }
+    }
+    __syncthreads();
+    if (t == 0) sm.n_list[cur] = 0;
+    __syncthreads();
+  }
+}
+
+// `emit(p, k, lb)` receives the bound of every live (parent p, slot k) of the tile's parents [rec_lo, rec_hi);
+// `dead(p, k)` is called for the slots below the live range (the evaluator zeroes them).
+template <int M, typename CT, typename Emit, typename Dead>
+__device__ __forceinline__ void lb2_compute_tile(Lb2Smem<M>& sm, const CT& C, const uint8_t* in_tile, int rec_lo,
+                                                 int rec_hi, int best, Emit&& emit, Dead&& dead) {
+  const int t = threadIdx.x;
+  const PfspLb1Tables& tab = sm.tab1;
+  const int jobs = tab.jobs;
+  const int32_t* nodes = reinterpret_cast<const int32_t*>(in_tile);
+
+  if (t < 2) sm.n_list[t] = 0;
+  __syncthreads();
+  // ---- phase A
+  if (t < LB2_TILE && t >= rec_lo && t < rec_hi) {
+    const int32_t* node = nodes + 22 * t;
+    const int limit1 = min(max(node[1], -1), PF_MAXJ - 1);
+    int F[M], R[M];
+    parent_front_remain<M>(tab, node, limit1, false, F, R);  // lb2 children always have limit1 >= 0
+#pragma unroll
+    for (int j = 0; j < M; j++) {
+      sm.front[j][t] = F[j];
+      sm.remain[j][t] = R[j];
+    }
+    uint32_t mask = 0;
+    for (int i = 0; i <= limit1; i++) mask |= 1u << node[2 + i];
+    sm.sched[t] = mask;
+    const int live = jobs - 1 - limit1;
+    int base = live > 0 ? atomicAdd(&sm.n_list[0], live) : 0;
+    for (int k = 0; k < jobs; k++) {
+      if (k > limit1)
+        sm.list[0][base++] = (static_cast<uint32_t>(t) << 24) | (static_cast<uint32_t>(k) << 16);
+      else
+        dead(t, k);
+    }
+  }
+  __syncthreads();
+  lb2_phase_b<M>(sm, C, nodes, best, emit);
+}
+
+template <int M, typename CT>
 __global__ void __launch_bounds__(PF_THREADS) pfsp_lb2_kernel(const uint8_t* __restrict__ parents,
                                                              uint8_t* __restrict__ bounds, long long count,
                                                              const PfspLb1Tables* __restrict__ tables1,
-                                                             const __grid_constant__ Lb2Const C, int best) {
+                                                             const __grid_constant__ CT C, int best) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  Lb2Smem& sm = *reinterpret_cast<Lb2Smem*>(smem_raw);
-  stage_blob(&sm.tab1, tables1, sizeof(PfspLb1Tables), &sm.tab_bar[0]);
+  Lb2Smem<M>& sm = *reinterpret_cast<Lb2Smem<M>*>(smem_raw);
+  lb2_stage_tables(sm, tables1, C);
   run_tile_pipeline<LB2_STAGES, LB2_TILE, PF_REC, PF_MAXJ * 4>(
       sm.tiles, parents, bounds, count, [&sm, &C, best](const uint8_t* in_tile, uint8_t* out_tile, int n, long long) {
         int32_t* out = reinterpret_cast<int32_t*>(out_tile);

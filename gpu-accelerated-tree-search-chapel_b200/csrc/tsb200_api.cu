@@ -435,6 +435,7 @@ int launch_nq_n(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cud
 
 int launch_nq(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
   if (h->N == 17 && h->variant == 1) return launch_nq_n<17, 1>(h, in, out, count, s);  // A/B experiment: byte alignment as IMAD.HI
+  if (h->N == 17 && h->variant == 2) return launch_nq_n<17, 2>(h, in, out, count, s);  // A/B experiment: bytes by LDS.U8
   switch (h->N) {
 #define TSB_NQ_CASE(n) \
   case n:              \
@@ -561,6 +562,8 @@ struct tsb_pfsp : Base {
   int jobs = 0, machines = 0, pairs = 0, mt = 0;  // mt = template machine count (5, 10 or 20)
   tsb::PfspLb1Tables* d_tab1 = nullptr;
   tsb::Lb2Const* lb2c = nullptr;  // packed Johnson tables, passed to the lb2 kernels by value (constant bank)
+  tsb::Lb2ConstU* lb2u = nullptr; // <= 10 machines: address of the shared-memory-resident table (tsb::Lb2TabU)
+  tsb::Lb2TabU* d_tabu = nullptr;
   bool attr_set[3] = {false, false, false};
   int occ[3] = {0, 0, 0};
   bool simd16 = false;  // lb1 / lb1_d children two per register (values < 2^16, min_tails non-increasing)
@@ -595,10 +598,10 @@ int launch_lb1_km(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count,
   return TSB_OK;
 }
 
-template <int M>
-int launch_lb2_m(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count, int best, cudaStream_t s) {
-  auto kernel = tsb::pfsp_lb2_kernel<M>;
-  const size_t smem = sizeof(tsb::Lb2Smem) + 128;
+template <int M, typename CT>
+int launch_lb2_mc(tsb_pfsp* h, const CT& C, const uint8_t* in, uint8_t* out, long long count, int best, cudaStream_t s) {
+  auto kernel = tsb::pfsp_lb2_kernel<M, CT>;
+  const size_t smem = sizeof(tsb::Lb2Smem<M>) + 128;
   if (!h->attr_set[2]) {
     TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     h->attr_set[2] = true;
@@ -606,10 +609,17 @@ int launch_lb2_m(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count, 
   int grid = 1;
   int rc = grid_for(kernel, tsb::PF_THREADS, smem, count, tsb::LB2_TILE, h->di.sms, &grid, &h->occ[2]);
   if (rc != TSB_OK) return rc;
-  kernel<<<grid, tsb::PF_THREADS, smem, s>>>(in, out, count, h->d_tab1, *h->lb2c, best);
+  kernel<<<grid, tsb::PF_THREADS, smem, s>>>(in, out, count, h->d_tab1, C, best);
   TSB_CUDA(cudaGetLastError());
   h->launches++;
   return TSB_OK;
+}
+template <int M>
+int launch_lb2_m(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count, int best, cudaStream_t s) {
+  if constexpr (M <= 10) {
+    if (h->lb2u) return launch_lb2_mc<M>(h, *h->lb2u, in, out, count, best, s);
+  }
+  return launch_lb2_mc<M>(h, *h->lb2c, in, out, count, best, s);
 }
 
 int launch_pfsp(tsb_pfsp* h, int lb_kind, const uint8_t* in, uint8_t* out, long long count, int64_t best64,
@@ -652,17 +662,28 @@ int pfsp_expand_m(tsb_pfsp* h, int lb_kind, const uint8_t* arena, const tsb::Exp
   if (rc != TSB_OK) return rc;
   if ((prm.n_tiles + g3 - 1) / g3 > tsb::EXP_MAX_OWN) return TSB_EINVAL;
   if (lb_kind == TSB_LB2) {
-    auto k1 = tsb::pfsp_expand_count_lb2_kernel<M>;
-    const size_t smem1 = sizeof(tsb::Lb2CountSmem) + 128;
-    if (!h->ex_attr[2]) {
-      TSB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
-      h->ex_attr[2] = true;
-    }
-    rc = grid_for(k1, tsb::PF_THREADS, smem1, recs, tsb::LB2_TILE, h->di.sms, &g1, &h->ex_occ[2]);
-    if (rc != TSB_OK) return rc;
+    const size_t smem1 = sizeof(tsb::Lb2CountSmem<M>) + 128;
     // (this kernel walks the round in half tiles and accumulates the tile counts)
     TSB_CUDA(cudaMemsetAsync(ex.d_tile, 0, static_cast<size_t>(prm.n_tiles) * sizeof(int), s));
-    k1<<<g1, tsb::PF_THREADS, smem1, s>>>(arena, prm, h->d_tab1, *h->lb2c, ex.d_cmask, ex.d_tile, ex.d_st);
+    auto go = [&](auto k1, const auto& C) -> int {
+      if (!h->ex_attr[2]) {
+        TSB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
+        h->ex_attr[2] = true;
+      }
+      int r2 = grid_for(k1, tsb::PF_THREADS, smem1, recs, tsb::LB2_TILE, h->di.sms, &g1, &h->ex_occ[2]);
+      if (r2 != TSB_OK) return r2;
+      k1<<<g1, tsb::PF_THREADS, smem1, s>>>(arena, prm, h->d_tab1, C, ex.d_cmask, ex.d_tile, ex.d_st);
+      return TSB_OK;
+    };
+    bool done = false;
+    if constexpr (M <= 10) {
+      if (h->lb2u) {
+        rc = go(tsb::pfsp_expand_count_lb2_kernel<M, tsb::Lb2ConstU>, *h->lb2u);
+        done = true;
+      }
+    }
+    if (!done) rc = go(tsb::pfsp_expand_count_lb2_kernel<M, tsb::Lb2Const>, *h->lb2c);
+    if (rc != TSB_OK) return rc;
   } else if (lb_kind == TSB_LB1) {
     auto k1 = h->simd16 ? tsb::pfsp_expand_count_lb1_kernel<1, M, true> : tsb::pfsp_expand_count_lb1_kernel<1, M, false>;
     const size_t smem1 = sizeof(tsb::Lb1CountSmem) + 128;
@@ -1092,6 +1113,26 @@ int tsb_pfsp_create(tsb_pfsp** out, int device, int jobs, int machines, int M_ma
                                           static_cast<uint32_t>(pb & 127) << 12 | static_cast<uint32_t>(lg & 8191) << 19;
     }
   }
+  // one-word-per-use table for the lb2 kernels of instances with <= 10 machines (env TSB200_NO_LB2U=1 disables)
+  std::vector<tsb::Lb2TabU> tuv;
+  const char* no_u = std::getenv("TSB200_NO_LB2U");
+  if (rc == TSB_OK && !bad && !wide && nb_pairs > 0 && nb_pairs <= tsb::LB2U_PAIRS && h->mt <= 10 && h->simd16 &&
+      !(no_u && *no_u && *no_u != '0')) {
+    tuv.resize(1);
+    tsb::Lb2TabU& tu = tuv[0];
+    std::memset(&tu, 0, sizeof(tu));
+    for (int l = 0; l < nb_pairs; l++) {
+      const int i = mp_order[l], a = mp0[i], b = mp1[i];
+      tu.mach[l] = static_cast<uint32_t>(a) | static_cast<uint32_t>(b) << 8;
+      tu.tails[l] = static_cast<uint32_t>(min_tails[a]) | static_cast<uint32_t>(min_tails[b]) << 16;
+      for (int j = 0; j < jobs; j++) {
+        const int job = johnson[i * jobs + j];
+        const int pa = p_times[a * jobs + job], pb = p_times[b * jobs + job], lg = lags[i * jobs + job];
+        tu.e[l * tsb::PF_MAXJ + j] = make_uint4(1u << job, static_cast<uint32_t>(pa + lg),
+                                                 static_cast<uint32_t>(pa - pb), 0u);
+      }
+    }
+  }
   if (rc == TSB_OK && bad) rc = TSB_EINVAL;
   if (rc == TSB_OK && wide) {  // processing times > 127 / lags > 8191 (outside the Taillard range): no lb2 on this handle
     delete h->lb2c;
@@ -1101,6 +1142,11 @@ int tsb_pfsp_create(tsb_pfsp** out, int device, int jobs, int machines, int M_ma
   auto upload = [&]() -> int {
     TSB_CUDA(cudaMalloc(&h->d_tab1, sizeof(t1)));
     TSB_CUDA(cudaMemcpyAsync(h->d_tab1, &t1, sizeof(t1), cudaMemcpyHostToDevice, h->stream));
+    if (!tuv.empty()) {
+      TSB_CUDA(cudaMalloc(&h->d_tabu, sizeof(tsb::Lb2TabU)));
+      TSB_CUDA(cudaMemcpyAsync(h->d_tabu, tuv.data(), sizeof(tsb::Lb2TabU), cudaMemcpyHostToDevice, h->stream));
+      h->lb2u = new (std::nothrow) tsb::Lb2ConstU{h->d_tabu};
+    }
     TSB_CUDA(cudaStreamSynchronize(h->stream));
     return TSB_OK;
   };
@@ -1119,6 +1165,8 @@ void tsb_pfsp_destroy(tsb_pfsp* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->d_tab1) cudaFree(h->d_tab1);
   delete h->lb2c;
+  delete h->lb2u;
+  if (h->d_tabu) cudaFree(h->d_tabu);
   h->ex.release();
   if (h->d_children) cudaFree(h->d_children);
   h->pool.release();
