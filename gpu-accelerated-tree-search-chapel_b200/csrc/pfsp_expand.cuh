@@ -160,10 +160,10 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_expand_count_lb2_kernel(const
   ExpandParams half = prm;
   for (int i = 0; i < half.n_pieces; i++) {
     // a piece's first build tile starts at first_tile*128 = (2*first_tile)*64
-    half.piece[i].first_tile *= 2;
-    half.piece[i].tile_cum *= 2;
+    half.piece[i].first_tile *= PF_TILE / LB2_TILE;
+    half.piece[i].tile_cum *= PF_TILE / LB2_TILE;
   }
-  half.n_tiles *= 2;
+  half.n_tiles *= PF_TILE / LB2_TILE;
   run_piece_tiles<2, LB2_TILE, PF_REC>(
       sm.core.tiles.in[0], sm.core.tiles.full, arena, half,
       [&](const uint8_t* in_tile, int lin, long long at, long long lo, long long hi) {
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_expand_count_lb2_kernel(const
         __syncthreads();
         if (t == 0) {
           const int tot = sm.red[0] + sm.red[1] + sm.red[2] + sm.red[3];
-          if (tot & 0xFFFF) atomicAdd(&tile_sums[lin >> 1], tot & 0xFFFF);
+          if (tot & 0xFFFF) atomicAdd(&tile_sums[lin / (PF_TILE / LB2_TILE)], tot & 0xFFFF);
           my_solutions += static_cast<unsigned>(tot >> 16);
         }
         if (t < LB2_TILE) cmask[static_cast<long long>(lin) * LB2_TILE + t] = m;

@@ -358,9 +358,15 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_lb1_kernel(const uint8_t* __r
 // re-appends the child to the next list unless its bound already exceeds `best` — about 90 % of the
 // children are pruned within the first pairs, and compacting the survivors keeps the warps full (v1 kept
 // a whole warp busy for all pairs as soon as one of its 32 children survived).
-constexpr int LB2_TILE = 64;
+#ifndef TSB_LB2_TILE
+#define TSB_LB2_TILE 64
+#endif
+#ifndef TSB_LB2_CHUNK
+#define TSB_LB2_CHUNK 9
+#endif
+constexpr int LB2_TILE = TSB_LB2_TILE;
 constexpr int LB2_STAGES = 2;
-constexpr int LB2_CHUNK = 5;  // machine pairs between two compactions
+constexpr int LB2_CHUNK = TSB_LB2_CHUNK;  // machine pairs between two compactions
 struct Lb2Const {
   uint32_t pair[PF_MAXP + 2];
   uint32_t jp[PF_MAXP * PF_MAXJ];
