@@ -150,7 +150,8 @@ __device__ __forceinline__ void expand_publish(const ScanSmem& sc, ExpandState* 
     res->children = static_cast<unsigned long long>(sc.total);
     res->solutions = st->solutions;
     res->best = st->best;
-    res->epoch = epoch;
+    __threadfence_system();  // the host may be polling `epoch` while this kernel still builds the children:
+    *reinterpret_cast<volatile unsigned long long*>(&res->epoch) = epoch;  // payload first, then the flag
     st->solutions = 0ull;  // the next round's count kernel starts after this kernel
     if (reset_best) st->best = 0x7FFFFFFF;
   }

@@ -318,6 +318,29 @@ struct ExpandCtx {
     }
     return TSB_OK;
   }
+  // Wait for the round's result record.  `early`: return as soon as the build kernel's first CTA has published
+  // the counts (it does so in its prologue) — the children are still being written, which is fine for a caller
+  // whose next use of them is ordered on the same stream (the pool); the host then prepares and launches the next
+  // round while this one finishes, which hides the launch + synchronisation latency of small rounds.
+  int wait_result(unsigned want_epoch, cudaStream_t s, bool early) {
+    if (early) {
+      const volatile unsigned long long* ep = &h_res->epoch;
+      for (unsigned spin = 0;; spin++) {
+        if (*ep == want_epoch) return TSB_OK;
+        if ((spin & 1023u) == 1023u) {  // a faulted kernel never publishes: ask the stream now and then
+          const cudaError_t q = cudaStreamQuery(s);
+          if (q == cudaSuccess) return *ep == want_epoch ? TSB_OK : TSB_ECUDA;
+          if (q != cudaErrorNotReady) {
+            g_last_cuda_error = std::string("expand kernels: ") + cudaGetErrorString(q);
+            (void)cudaGetLastError();
+            return TSB_ECUDA;
+          }
+        }
+      }
+    }
+    TSB_CUDA(cudaStreamSynchronize(s));
+    return h_res->epoch == want_epoch ? TSB_OK : TSB_ECUDA;
+  }
   void release() {
     if (d_cmask) cudaFree(d_cmask);
     if (d_tile) cudaFree(d_tile);
@@ -477,7 +500,7 @@ int make_params(const std::vector<PoolExtent>& pieces, int tile_records, tsb::Ex
 // `children_d`.  Synchronous: the counts come back through the host-mapped result record.
 template <int N>
 int nq_expand_n(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& pieces, uint8_t* children_d,
-                cudaStream_t s, unsigned long long* n_children, unsigned long long* n_solutions) {
+                cudaStream_t s, unsigned long long* n_children, unsigned long long* n_solutions, bool early) {
   tsb::ExpandParams prm;
   int rc = make_params(pieces, tsb::NQ_TILE, &prm);
   if (rc != TSB_OK) return rc;
@@ -507,10 +530,10 @@ int nq_expand_n(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& 
   k3<<<g3, tsb::NQ_THREADS, smem3, s>>>(arena, prm, d_items, ex.d_tile, children_d, ex.d_st, ex.d_res);
   TSB_CUDA(cudaGetLastError());
   h->launches += 2;
-  TSB_CUDA(cudaStreamSynchronize(s));
-  if (ex.h_res->epoch != prm.epoch) {
-    g_last_cuda_error = "expand kernels did not publish their result";
-    return TSB_ECUDA;
+  rc = ex.wait_result(prm.epoch, s, early);
+  if (rc != TSB_OK) {
+    if (g_last_cuda_error.empty()) g_last_cuda_error = "expand kernels did not publish their result";
+    return rc;
   }
   *n_children = ex.h_res->children;
   *n_solutions = ex.h_res->solutions;
@@ -518,11 +541,11 @@ int nq_expand_n(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& 
 }
 
 int nq_expand_dispatch(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& pieces, uint8_t* children_d,
-                       cudaStream_t s, unsigned long long* nc, unsigned long long* ns) {
+                       cudaStream_t s, unsigned long long* nc, unsigned long long* ns, bool early = false) {
   switch (h->N) {
 #define TSB_NQ_CASE(n) \
   case n:              \
-    return nq_expand_n<n>(h, arena, pieces, children_d, s, nc, ns);
+    return nq_expand_n<n>(h, arena, pieces, children_d, s, nc, ns, early);
     TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
     TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
     TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
@@ -737,7 +760,7 @@ void pfsp_generate_children_host(int jobs, const tsb_pfsp_node* parents, int siz
 // n * jobs nodes).  *best is read and updated with the reference's semantics.  Synchronous.
 int pfsp_expand_round(tsb_pfsp* h, int lb_kind, const uint8_t* arena, const std::vector<PoolExtent>& pieces,
                       uint8_t* children_d, cudaStream_t s, int64_t* best, unsigned long long* n_children,
-                      unsigned long long* n_solutions) {
+                      unsigned long long* n_solutions, bool early = false) {
   tsb::ExpandParams prm;
   int rc = make_params(pieces, tsb::PF_TILE, &prm);
   if (rc != TSB_OK) return rc;
@@ -754,10 +777,10 @@ int pfsp_expand_round(tsb_pfsp* h, int lb_kind, const uint8_t* arena, const std:
   else
     rc = pfsp_expand_m<20>(h, lb_kind, arena, prm, children_d, s);
   if (rc != TSB_OK) return rc;
-  TSB_CUDA(cudaStreamSynchronize(s));
-  if (ex.h_res->epoch != prm.epoch) {
-    g_last_cuda_error = "expand kernels did not publish their result";
-    return TSB_ECUDA;
+  rc = ex.wait_result(prm.epoch, s, early);
+  if (rc != TSB_OK) {
+    if (g_last_cuda_error.empty()) g_last_cuda_error = "expand kernels did not publish their result";
+    return rc;
   }
   if (ex.h_res->best >= best_launch) {  // no leaf of the chunk improved best: the launch-value masks are exact
     *n_children = ex.h_res->children;
@@ -976,7 +999,7 @@ int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_ch
   const long long top = p.top();
   unsigned long long nc = 0, ns = 0;
   uint8_t* arena = p.arena[p.cur];
-  rc = nq_expand_dispatch(h, arena, pieces, arena + top * sizeof(tsb_nq_node), h->stream, &nc, &ns);
+  rc = nq_expand_dispatch(h, arena, pieces, arena + top * sizeof(tsb_nq_node), h->stream, &nc, &ns, /*early=*/true);
   if (rc != TSB_OK) return rc;
   pool_pop(p, n);
   if (nc) {
@@ -1299,7 +1322,8 @@ int tsb_pfsp_pool_step(tsb_pfsp* h, int lb_kind, int m, int M, int64_t* best, in
   const long long top = (p.top() + 1) & ~1LL;  // children start on a 16-byte boundary (88 B records)
   unsigned long long nc = 0, ns = 0;
   uint8_t* arena = p.arena[p.cur];
-  rc = pfsp_expand_round(h, lb_kind, arena, pieces, arena + top * sizeof(tsb_pfsp_node), h->stream, best, &nc, &ns);
+  rc = pfsp_expand_round(h, lb_kind, arena, pieces, arena + top * sizeof(tsb_pfsp_node), h->stream, best, &nc, &ns,
+                         /*early=*/true);
   if (rc != TSB_OK) return rc;
   pool_pop(p, n);
   if (nc) {
