@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -160,9 +161,15 @@ void nq_gpu_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool
 // generate_children of a round are one kernel; the host reads three counters per round
 void nq_devpool_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResult& r) {
   tsb_nq* h = nullptr;
+  const bool trace = std::getenv("TSB200_TRACE") != nullptr;
+  const double tt0 = now_s();
   r.rc = tsb_nq_create(&h, device, N, g, M);
   if (r.rc != TSB_OK) return;
+  const double tt1 = now_s();
   r.rc = tsb_nq_pool_push(h, &pool.el[pool.front], static_cast<int64_t>(pool.size));
+  const double tt2 = now_s();
+  if (trace) std::fprintf(stderr, "[tsb200] device %d: create %.1f ms, first push (arena) %.1f ms\n", device,
+                          (tt1 - tt0) * 1e3, (tt2 - tt1) * 1e3);
   pool.front = 0;
   pool.size = 0;
   while (r.rc == TSB_OK) {
@@ -174,7 +181,12 @@ void nq_devpool_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& 
     r.sol += ns;
     ++r.offloads;
     r.parents += static_cast<uint64_t>(np);
+    if (trace && (r.offloads == 1 || r.offloads == 10 || r.offloads == 100 || r.offloads == 1000))
+      std::fprintf(stderr, "[tsb200] device %d: %llu rounds after %.1f ms\n", device,
+                   static_cast<unsigned long long>(r.offloads), (now_s() - tt2) * 1e3);
   }
+  if (trace) std::fprintf(stderr, "[tsb200] device %d: %llu rounds in %.1f ms\n", device,
+                          static_cast<unsigned long long>(r.offloads), (now_s() - tt2) * 1e3);
   if (r.rc == TSB_OK) {  // fewer than m nodes left: back to the host pool for step 3
     const int64_t left = tsb_nq_pool_size(h);
     std::vector<tsb_nq_node> rest(static_cast<size_t>(left) + 1);
