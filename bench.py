@@ -524,7 +524,8 @@ def main():
                              "launch, launch-latency bound by construction (SURVEY.md hard part 2)"}
     if not args.no_pfsp:
         pf = run_workload("pfsp", args.pfsp_M, args.steps, args.warmup, device_index, world)
-        ps = summarize(pf, peak, peak_src)
+        # DRAM bytes of one launch of this shape (ta014, 1 Mi parents): profiles/pfsp_lb1_r1_ncu.txt
+        ps = summarize(pf, peak, peak_src, traffic=92355072 + 27396096 if args.pfsp_M == 1 << 20 else None)
         line["pfsp"] = {"workload": "PFSP ta014 lb1 ub=1, synthetic parents with the ta014/lb1 offload depth histogram",
                         "M": args.pfsp_M, "value": ps["value"], "unit": "Mnodes/s", "ms_per_step": ps["ms_per_step"],
                         "e2e": ps["e2e"], "roofline": ps["roofline"], "gpu_launches": pf["launches"],
@@ -535,7 +536,7 @@ def main():
             line["pfsp"]["at_M50000"] = {"value": s2["value"], "e2e": s2["e2e"], "roofline": s2["roofline"]}
     if args.lb2:
         l2 = run_workload("lb2", 1 << 18, max(3, args.steps // 10), args.warmup, device_index, world)
-        ls = summarize(l2, peak, peak_src)
+        ls = summarize(l2, peak, peak_src, traffic=23106048 + 512)  # profiles/pfsp_lb2_r1_ncu.txt (bounds stay in L2)
         line["pfsp_lb2"] = {"workload": "PFSP ta020 lb2 ub=1 (best=1591 at launch), synthetic parents with the "
                             "ta020/lb2 offload depth histogram; int-ALU bound (O(pairs*jobs) per child)",
                             "M": 1 << 18, "value": ls["value"], "unit": "Mnodes/s", "ms_per_step": ls["ms_per_step"],
