@@ -548,8 +548,9 @@ def main():
                 "scaling": "strong" if world > 1 else None,
                 "nqueens_N17": run_search("nq", world, rank, device_index, reps, N=17, M=args.M),
                 "nqueens_N17_M50000": run_search("nq", world, rank, device_index, 1, N=17, M=50000),
-                "pfsp_ta014_lb1_M50000": run_search("pfsp", world, rank, device_index, reps, inst=14, lb="lb1", M=50000),
-                "pfsp_ta020_lb2_M50000": run_search("pfsp", world, rank, device_index, reps, inst=20, lb="lb2", M=50000)}
+                # (millisecond-scale searches: more repetitions, a sporadic slow cudaMalloc is tens of ms)
+                "pfsp_ta014_lb1_M50000": run_search("pfsp", world, rank, device_index, 7, inst=14, lb="lb1", M=50000),
+                "pfsp_ta020_lb2_M50000": run_search("pfsp", world, rank, device_index, 7, inst=20, lb="lb2", M=50000)}
         line["search"] = srch
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
