@@ -113,7 +113,7 @@ int tsb_nq_expand_device(tsb_nq* h, const void* parents_d /*16-B aligned*/, int 
 
 /* ---- device-resident pool: the reference's SinglePool (lib/commons/Pool.chpl) kept in
  * HBM.  push = pushBack of host nodes; step = one offload round of nqueens_gpu_chpl.chpl:197-215 done
- * entirely on the device by ONE kernel: popBackBulk(m, M) (nothing below m, else the newest min(size, M)
+ * entirely on the device (two kernels: count + build): popBackBulk(m, M) (nothing below m, else the newest min(size, M)
  * nodes, order preserved, read in place), evaluate, generate_children appended to the pool; drain = move what
  * is left to the host (logical order).  The pool's logical content after every round is byte-identical to
  * the reference's host pool. */
