@@ -158,7 +158,7 @@ void nq_gpu_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool
 }
 
 // the same loop with the task's pool resident on the device (tsb_nq_pool_*): popBackBulk, evaluate and
-// generate_children of a round are one kernel; the host reads three counters per round
+// generate_children of a round are two kernels (count, build); the host reads three counters per round
 void nq_devpool_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResult& r) {
   tsb_nq* h = nullptr;
   const bool trace = std::getenv("TSB200_TRACE") != nullptr;
