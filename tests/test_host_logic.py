@@ -78,3 +78,20 @@ def test_taillard_shapes():
     for inst in range(1, 121):
         assert L.tsb_taillard_nb_jobs(inst) == po.lib().or_taillard_nb_jobs(inst)
         assert L.tsb_taillard_nb_machines(inst) == po.lib().or_taillard_nb_machines(inst)
+
+
+def test_chapel_binding_declares_only_exported_symbols_with_matching_arity():
+    """chapel/TSB200.chpl cannot be compiled here (no chpl): at least keep its extern procs in step with the header —
+    every extern proc must exist in include/tsb200.h with the same number of parameters"""
+    header = open(os.path.join(ROOT, "include", "tsb200.h")).read()
+    chpl = open(os.path.join(ROOT, "gpu-accelerated-tree-search-chapel_b200", "chapel", "TSB200.chpl")).read()
+    decls = {}
+    for m in re.finditer(r"\b(tsb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        args = m.group(2).strip()
+        decls[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    externs = re.findall(r"extern proc (tsb_[a-z0-9_]+)\s*\((.*?)\)\s*(?::|;)", chpl, flags=re.S)
+    assert len(externs) >= 15
+    for name, args in externs:
+        assert name in decls, f"{name} is not declared in include/tsb200.h"
+        n = 0 if not args.strip() else args.count(",") + 1
+        assert n == decls[name], f"{name}: {n} parameters in TSB200.chpl, {decls[name]} in the header"
