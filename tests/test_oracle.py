@@ -123,3 +123,59 @@ def test_pfsp_search_counts_ta014(counts, lb):
     for (m, M, D) in ((25, 50000, 1), (25, 50000, 4)):
         r = po.pfsp_search_offload(14, lb, 1, m, M, D)
         assert (r.tree, r.sol, r.best) == (want["tree"], want["sol"], want["best"]), (m, M, D)
+
+
+# ---- the chunk-level oracle functions the GPU expand / pool tests compare against, pinned on the driver-level ones
+def _pool_search(expand, start, m, M):
+    """the reference's step-2 loop (popBackBulk(m, M) -> evaluate -> generate_children -> pushBack) on a numpy pool"""
+    pool, tree, sol, offloads, parents = start, 0, 0, 0, 0
+    while pool.shape[0] >= m:
+        n = min(pool.shape[0], M)
+        chunk = np.ascontiguousarray(pool[pool.shape[0] - n:])
+        kids, s = expand(chunk)
+        pool = np.concatenate([pool[: pool.shape[0] - n], kids])
+        tree, sol, offloads, parents = tree + kids.shape[0], sol + s, offloads + 1, parents + n
+    return pool, tree, sol, offloads, parents
+
+
+@pytest.mark.parametrize("N,m,M", [(10, 25, 50000), (11, 5, 300)])
+def test_nq_expand_chunk_reproduces_the_offload_search(counts, N, m, M):
+    """a pool driven by or_nq_expand_chunk from the warm-up pool of the driver = the driver's own step 2"""
+    ref = po.nq_search_offload(N, 1, m, M, 1)
+    # warm-up (step 1): breadth-first from the root until the pool holds m nodes, as the driver does
+    root = np.zeros(1, dtype=po.NQ_NODE_DTYPE)
+    root["board"][0, :N] = np.arange(N)
+    pool, tree1, sol1 = root, 0, 0
+    while pool.shape[0] < m and pool.shape[0] > 0:
+        kids, s = po.nq_expand(np.ascontiguousarray(pool[:1]), N)
+        pool = np.concatenate([pool[1:], kids])
+        tree1, sol1 = tree1 + kids.shape[0], sol1 + s
+    rest, tree2, sol2, offloads, parents = _pool_search(lambda c: po.nq_expand(c, N), pool, m, M)
+    assert (offloads, parents) == (ref.offloads, ref.offloaded_parents)
+    # step 3: drain what is left depth-first (order does not matter for the counts)
+    tree3 = sol3 = 0
+    while rest.shape[0]:
+        kids, s = po.nq_expand(np.ascontiguousarray(rest), N)
+        rest, tree3, sol3 = kids, tree3 + kids.shape[0], sol3 + s
+    want = counts["nqueens"][str(N)]
+    assert (tree1 + tree2 + tree3, sol1 + sol2 + sol3) == (want["tree"], want["sol"]) == (ref.tree, ref.sol)
+
+
+@pytest.mark.parametrize("lb", [0, 1])
+def test_pfsp_expand_chunk_reproduces_the_offload_search(lb):
+    """or_pfsp_expand_chunk (bounds with best at launch + sequential generate_children) driven as a pool from a
+    captured first chunk equals the driver emulation from that point on: same number of offloads and parents"""
+    inst, m, M = 14, 25, 50000
+    t = po.tables(inst, heads_mode=0)
+    ref = po.pfsp_search_offload(inst, lb, 1, m, M, 1)
+    first, best = po.pfsp_capture_chunk(inst, lb, 0, 1, m, M)  # the whole warm-up pool (it is < M)
+    state = {"best": best}
+
+    def expand(chunk):
+        kids, s, b = po.pfsp_expand(t, lb, chunk, state["best"])
+        state["best"] = b
+        return kids, s
+
+    rest, tree2, sol2, offloads, parents = _pool_search(expand, first, m, M)
+    assert (offloads, parents) == (ref.offloads, ref.offloaded_parents)
+    assert state["best"] == ref.best == 1377
