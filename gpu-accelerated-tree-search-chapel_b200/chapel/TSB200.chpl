@@ -33,6 +33,13 @@ module TSB200 {
   extern proc tsb_nq_evaluate(h: c_ptr(tsb_nq), parents: c_ptrConst(void), count: c_int,
                               labels: c_ptr(uint(8))): c_int;
 
+  // optional, once per search: page-lock + map the driver's long-lived `parents` / `labels` (`bounds`) arrays
+  // so that tsb_*_evaluate works on them in place (zero-copy); they must outlive the handle
+  extern proc tsb_nq_register_host(h: c_ptr(tsb_nq), p: c_ptr(void), bytes: c_size_t): c_int;
+  extern proc tsb_nq_unregister_host(h: c_ptr(tsb_nq), p: c_ptr(void)): c_int;
+  extern proc tsb_pfsp_register_host(h: c_ptr(tsb_pfsp), p: c_ptr(void), bytes: c_size_t): c_int;
+  extern proc tsb_pfsp_unregister_host(h: c_ptr(tsb_pfsp), p: c_ptr(void)): c_int;
+
   extern proc tsb_pfsp_create(ref h: c_ptr(tsb_pfsp), device: c_int, jobs: c_int, machines: c_int,
                               M_max: c_int, p_times: c_ptrConst(int(32)), min_heads: c_ptrConst(int(32)),
                               min_tails: c_ptrConst(int(32)), nb_pairs: c_int,
@@ -51,6 +58,8 @@ module TSB200 {
   extern proc tsb_nq_pool_size(h: c_ptr(tsb_nq)): int(64);
   extern proc tsb_nq_pool_step(h: c_ptr(tsb_nq), m: c_int, M: c_int, ref n_parents: int(64),
                                ref n_children: uint(64), ref n_solutions: uint(64)): c_int;
+  extern proc tsb_nq_pool_run(h: c_ptr(tsb_nq), m: c_int, M: c_int, max_rounds: int(64), ref n_rounds: uint(64),
+                              ref n_parents: uint(64), ref n_children: uint(64), ref n_solutions: uint(64)): c_int;
   extern proc tsb_nq_pool_drain(h: c_ptr(tsb_nq), nodes: c_ptr(void), capacity_nodes: int(64),
                                 ref n: int(64)): c_int;
   extern proc tsb_pfsp_expand(h: c_ptr(tsb_pfsp), lb_kind: c_int, parents: c_ptrConst(void), count: c_int,

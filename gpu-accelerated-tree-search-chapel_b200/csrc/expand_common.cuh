@@ -88,7 +88,7 @@ __device__ __forceinline__ void copy_image_to_global(uint8_t* gdst, const uint8_
 __device__ __forceinline__ uint32_t tile_load_bytes(long long abs_tile, long long hi, int tile_records, int rec) {
   const long long b = (hi - abs_tile * tile_records) * rec;
   const long long full = static_cast<long long>(tile_records) * rec;
-  if (b <= 0) return 16u;  // a (half) tile that lies wholly past the piece's end: nothing of it is used
+  if (b <= 0) return 0u;  // a (half) tile that lies wholly past the piece's end: nothing to load
   return static_cast<uint32_t>(b >= full ? full : (b + 15) & ~15LL);
 }
 

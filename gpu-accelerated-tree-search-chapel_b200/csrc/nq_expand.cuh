@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(NQ_THREADS) nq_expand_count_kernel(const uint8
     piece_of(prm, lin, NQ_TILE, at, lo, hi);
     const uint32_t nb = tile_load_bytes(at, hi, NQ_TILE, NQ_REC);
     mbar_arrive_expect_tx(&sm.full[s], nb);
-    bulk_g2s(sm.in[s], arena + at * IN_BYTES, nb, &sm.full[s]);  // default L2 policy: the build kernel re-reads it
+    if (nb) bulk_g2s(sm.in[s], arena + at * IN_BYTES, nb, &sm.full[s]);  // default L2 policy: the build kernel re-reads it
   };
   if (t == 0) {
     if (first < prm.n_tiles) issue(first, 0);
@@ -191,12 +191,12 @@ struct NqBuildSmem {
 };
 
 // child `c` of the tile -> bytes [B, B + 21) of the staging image (B = image offset of the child).  The parent
-// record sits at byte 21*r of the tile, i.e. at byte (r & 3) of an aligned word.
+// record sits at byte 21*r of the tile (any alignment: the slices of nq_rounds.cuh start at any byte).
 __device__ __forceinline__ void nq_build_child(const uint8_t* in_tile, int item, uint8_t* image, int B) {
   const int r = item >> 5, k = item & 31;
   const uint8_t* src = in_tile + r * NQ_REC;
-  const uint32_t a8 = (r & 3) * 8;
-  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - (r & 3));
+  const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src)) & 3u, a8 = mis * 8u;  // (= r & 3 for an aligned tile)
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - mis);
   const uint32_t s0 = sw[0], s1 = sw[1], s2 = sw[2], s3 = sw[3], s4 = sw[4], s5 = sw[5];
   // parent-aligned words: P[j] = parent bytes 4j .. 4j+3 (P5: byte 20 only)
   uint32_t P[6] = {shf_r_wrap(s0, s1, a8), shf_r_wrap(s1, s2, a8), shf_r_wrap(s2, s3, a8),
@@ -250,8 +250,8 @@ __device__ __forceinline__ void nq_build_child_warp(const uint8_t* in_tile, int 
   if (active) {
     const int r = item >> 5, k = item & 31;
     const uint8_t* src = in_tile + r * NQ_REC;
-    const uint32_t a8 = (r & 3) * 8;
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - (r & 3));
+    const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src)) & 3u, a8 = mis * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - mis);
     const uint32_t s0 = sw[0], s1 = sw[1], s2 = sw[2], s3 = sw[3], s4 = sw[4], s5 = sw[5];
     uint32_t P[6] = {shf_r_wrap(s0, s1, a8), shf_r_wrap(s1, s2, a8), shf_r_wrap(s2, s3, a8),
                      shf_r_wrap(s3, s4, a8), shf_r_wrap(s4, s5, a8), shf_r_wrap(s5, 0u, a8) & 0xFFu};
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NQ_THREADS) nq_expand_build_kernel(const uint8
     piece_of(prm, lin, NQ_TILE, at, lo, hi);
     const uint32_t nb = tile_load_bytes(at, hi, NQ_TILE, NQ_REC);
     mbar_arrive_expect_tx(&sm.full[s], nb);
-    bulk_g2s_stream(sm.in[s], arena + at * IN_BYTES, nb, &sm.full[s], pol);
+    if (nb) bulk_g2s_stream(sm.in[s], arena + at * IN_BYTES, nb, &sm.full[s], pol);
   };
   auto issue_items = [&](int lin, int s, int cnt) {  // thread 0: the first window of the tile's items
     const uint32_t nb = (static_cast<uint32_t>(min(cnt, EXP_CAP)) * 2u + 15u) & ~15u;

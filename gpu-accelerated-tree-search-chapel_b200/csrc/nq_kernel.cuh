@@ -42,8 +42,10 @@ constexpr int NQ_TILE = NQ_THREADS * NQ_QUAD;    // 512 parents per tile
 constexpr int NQ_REC = 21;                       // sizeof(tsb_nq_node)
 constexpr int NQ_STAGES = 2;
 
-template <int N>
-using NqSmem = TileSmem<NQ_STAGES, NQ_TILE * NQ_REC, NQ_TILE * N>;
+// (T = threads per CTA, 4 parents each: 128 for bandwidth-bound batches; 64 / 32 give small chunks — the
+// reference's default --M 50000 is 97 tiles of 512 — enough CTAs to cover all SMs)
+template <int N, int T = NQ_THREADS>
+using NqSmem = TileSmem<NQ_STAGES, T * NQ_QUAD * NQ_REC, T * NQ_QUAD * N>;
 
 // Integer multiplies that must stay multiplies: they run on the FMA pipe (IMAD), which this
 // kernel leaves idle, instead of the ALU pipe (SHF/LOP3), which is its bottleneck.
@@ -224,12 +226,12 @@ __device__ __forceinline__ void nq_compute_tile(const uint8_t* in_tile, uint8_t*
   for (int i = 0; i < N; i++) out_w[i] = o[i];
 }
 
-template <int N, int VAR>
-__global__ void __launch_bounds__(NQ_THREADS) nq_evaluate_kernel(const uint8_t* __restrict__ parents,
-                                                                uint8_t* __restrict__ labels, long long count) {
+template <int N, int VAR, int T = NQ_THREADS>
+__global__ void __launch_bounds__(T) nq_evaluate_kernel(const uint8_t* __restrict__ parents,
+                                                       uint8_t* __restrict__ labels, long long count) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  NqSmem<N>& sm = *reinterpret_cast<NqSmem<N>*>(smem_raw);
-  run_tile_pipeline<NQ_STAGES, NQ_TILE, NQ_REC, N>(
+  NqSmem<N, T>& sm = *reinterpret_cast<NqSmem<N, T>*>(smem_raw);
+  run_tile_pipeline<NQ_STAGES, T * NQ_QUAD, NQ_REC, N>(
       sm, parents, labels, count,
       [](const uint8_t* in_tile, uint8_t* out_tile, int n, long long) { nq_compute_tile<N, VAR>(in_tile, out_tile, n); });
 }

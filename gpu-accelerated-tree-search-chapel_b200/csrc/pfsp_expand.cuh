@@ -45,7 +45,8 @@ __device__ __forceinline__ void run_piece_tiles(uint8_t* in /* STAGES x TILE*REC
     piece_of(prm, lin, TILE, at, lo, hi);
     const uint32_t nb = tile_load_bytes(at, hi, TILE, REC);
     mbar_arrive_expect_tx(&full[s], nb);
-    bulk_g2s(in + s * IN_BYTES, arena + at * IN_BYTES, nb, &full[s]);  // default L2 policy: the build kernel re-reads it
+    // (a half tile that lies wholly past the piece's end loads nothing: the phase completes on the arrival alone)
+    if (nb) bulk_g2s(in + s * IN_BYTES, arena + at * IN_BYTES, nb, &full[s]);  // default L2 policy: the build kernel re-reads it
   };
   if (t == 0)
     for (int s = 0; s < STAGES; s++)
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_expand_build_kernel(const uin
     piece_of(prm, lin, PF_TILE, at, lo, hi);
     const uint32_t nb = tile_load_bytes(at, hi, PF_TILE, PF_REC);
     mbar_arrive_expect_tx(&sm.full[s], nb + PF_TILE * 4);
-    bulk_g2s_stream(sm.in[s], arena + at * IN_BYTES, nb, &sm.full[s], pol);
+    if (nb) bulk_g2s_stream(sm.in[s], arena + at * IN_BYTES, nb, &sm.full[s], pol);
     bulk_g2s_stream(sm.mask[s], cmask + static_cast<long long>(lin) * PF_TILE, PF_TILE * 4, &sm.full[s], pol);
   };
   if (t == 0) {
@@ -314,6 +315,10 @@ __global__ void __launch_bounds__(PF_THREADS) pfsp_expand_build_kernel(const uin
         bulk_commit();
       }
     }
+    // a tile without children has no barrier after (A): without this one a fast warp could overwrite warp_tot
+    // for tile it+1 while a slow warp still reads the totals of tile it (and thread 0 could re-arm full[s] twice
+    // before a slow warp has tested the phase of tile it)
+    if (total == 0) __syncthreads();
     if (t == 0 && lin + 2 * stride < prm.n_tiles) issue(lin + 2 * stride, s);
   }
   if (t == 0) bulk_wait_all();

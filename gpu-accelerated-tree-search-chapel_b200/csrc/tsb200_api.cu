@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "nq_expand.cuh"
+#include "nq_rounds.cuh"
 #include "pfsp_expand.cuh"
 #include "nq_kernel.cuh"
 #include "pfsp_kernels.cuh"
@@ -50,8 +51,11 @@ bool env_no_register() {
   return s && *s && *s != '0';
 }
 
-// Host ranges kept page-locked + mapped between calls, so that cudaMemcpyAsync is truly
-// asynchronous on the caller's own arrays and the zero-copy kernels can address them.
+// Host ranges the CALLER asked to page-lock + map (tsb_*_register_host): cudaMemcpyAsync is truly asynchronous
+// on them and the zero-copy kernels can address them.  Registration is explicit and the caller owns the
+// lifetime: a range must stay allocated until it is unregistered or the handle is destroyed (a registration
+// keyed on an address alone goes stale when the array is freed and another one lands on the same addresses).
+// Arrays that were never registered go through the handle's own pinned staging buffers.
 struct HostRange {
   uintptr_t base;
   size_t len;
@@ -59,32 +63,33 @@ struct HostRange {
 struct HostRegistry {
   std::vector<HostRange> ranges;
   bool disabled = env_no_register();
-  // returns true if [p, p+bytes) is (now) page-locked
-  bool ensure(const void* p, size_t bytes) {
-    if (disabled || !p || !bytes) return false;
+  bool contains(const void* p, size_t bytes) const {
+    if (!p || !bytes) return false;
     const uintptr_t a = reinterpret_cast<uintptr_t>(p), b = a + bytes;
-    for (auto& r : ranges)
+    for (const auto& r : ranges)
       if (a >= r.base && b <= r.base + r.len) return true;
-    // merge with any overlapping registered range (the caller's array seen with a larger count)
-    uintptr_t na = a, nb = b;
-    for (size_t i = 0; i < ranges.size();) {
-      const uintptr_t ra = ranges[i].base, rb = ra + ranges[i].len;
-      if (ra < nb && na < rb) {
-        cudaHostUnregister(reinterpret_cast<void*>(ra));
-        na = std::min(na, ra);
-        nb = std::max(nb, rb);
+    return false;
+  }
+  // TSB_OK, or TSB_EINVAL for a range that partly overlaps a registered one, or TSB_ECUDA
+  int add(void* p, size_t bytes) {
+    if (!p || !bytes) return TSB_EINVAL;
+    if (disabled || contains(p, bytes)) return TSB_OK;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p), b = a + bytes;
+    for (const auto& r : ranges)
+      if (r.base < b && a < r.base + r.len) return TSB_EINVAL;
+    TSB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    ranges.push_back({a, bytes});
+    return TSB_OK;
+  }
+  int remove(void* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    for (size_t i = 0; i < ranges.size(); i++)
+      if (ranges[i].base == a) {
+        cudaHostUnregister(p);
         ranges.erase(ranges.begin() + i);
-      } else {
-        ++i;
+        return TSB_OK;
       }
-    }
-    if (cudaHostRegister(reinterpret_cast<void*>(na), nb - na, cudaHostRegisterPortable | cudaHostRegisterMapped) !=
-        cudaSuccess) {
-      (void)cudaGetLastError();
-      return false;
-    }
-    ranges.push_back({na, nb - na});
-    return true;
+    return disabled ? TSB_OK : TSB_EINVAL;
   }
   void release() {
     for (auto& r : ranges) cudaHostUnregister(reinterpret_cast<void*>(r.base));
@@ -95,6 +100,7 @@ struct HostRegistry {
 struct DeviceInfo {
   int sms = 0;
   bool can_use_host_ptr = false;
+  bool coop = false;  // cooperative launches (the persistent multi-round kernel)
 };
 int query_device(int device, DeviceInfo& di) {
   int n = 0;
@@ -108,6 +114,8 @@ int query_device(int device, DeviceInfo& di) {
   int v = 0;
   TSB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrCanUseHostPointerForRegisteredMem, device));
   di.can_use_host_ptr = v != 0;
+  TSB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, device));
+  di.coop = v != 0;
   return TSB_OK;
 }
 
@@ -154,45 +162,67 @@ struct Base {
     if (h_in) cudaFreeHost(h_in);
     if (h_out) cudaFreeHost(h_out);
     if (bounce) cudaFreeHost(bounce);
+    if (bounce_ev[0]) cudaEventDestroy(bounce_ev[0]);
+    if (bounce_ev[1]) cudaEventDestroy(bounce_ev[1]);
     if (stream) cudaStreamDestroy(stream);
     if (stream2) cudaStreamDestroy(stream2);
   }
 
-  // Copies between a caller-owned host range and the device, on `stream`, synchronous.  A plain cudaMemcpy on
-  // a host range that only partly overlaps a range this handle page-locked earlier (a previous caller array
-  // at the same addresses) fails with "invalid argument", so: small copies bounce through a pinned buffer,
-  // large ones are page-locked first (which merges them with whatever they overlap).
+  // Copies between a caller-owned host range and the device, ordered on stream `s` (the stream the kernels
+  // that produce / consume the data run on), synchronous.  Registered ranges are copied directly; anything else
+  // bounces through two pinned buffers so that the host memcpy of one piece overlaps the DMA of the previous one.
   uint8_t* bounce = nullptr;
+  cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
   static constexpr size_t kBounce = 1 << 20;
-  int copy_h2d(void* dst_d, const void* src_h, size_t bytes) {
-    if (!bytes) return TSB_OK;
-    if (bytes > kBounce && reg.ensure(src_h, bytes)) {
-      TSB_CUDA(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, stream));
-      TSB_CUDA(cudaStreamSynchronize(stream));
-      return TSB_OK;
-    }
-    if (!bounce) TSB_CUDA(cudaHostAlloc(&bounce, kBounce, cudaHostAllocPortable));
-    for (size_t off = 0; off < bytes; off += kBounce) {
-      const size_t n = std::min(kBounce, bytes - off);
-      std::memcpy(bounce, static_cast<const uint8_t*>(src_h) + off, n);
-      TSB_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst_d) + off, bounce, n, cudaMemcpyHostToDevice, stream));
-      TSB_CUDA(cudaStreamSynchronize(stream));
+  int ensure_bounce() {
+    if (!bounce) {
+      TSB_CUDA(cudaHostAlloc(&bounce, 2 * kBounce, cudaHostAllocPortable));
+      TSB_CUDA(cudaEventCreateWithFlags(&bounce_ev[0], cudaEventDisableTiming));
+      TSB_CUDA(cudaEventCreateWithFlags(&bounce_ev[1], cudaEventDisableTiming));
     }
     return TSB_OK;
   }
-  int copy_d2h(void* dst_h, const void* src_d, size_t bytes) {
+  int copy_h2d(void* dst_d, const void* src_h, size_t bytes, cudaStream_t s) {
     if (!bytes) return TSB_OK;
-    if (bytes > kBounce && reg.ensure(dst_h, bytes)) {
-      TSB_CUDA(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, stream));
-      TSB_CUDA(cudaStreamSynchronize(stream));
+    if (reg.contains(src_h, bytes)) {
+      TSB_CUDA(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, s));
+      TSB_CUDA(cudaStreamSynchronize(s));
       return TSB_OK;
     }
-    if (!bounce) TSB_CUDA(cudaHostAlloc(&bounce, kBounce, cudaHostAllocPortable));
-    for (size_t off = 0; off < bytes; off += kBounce) {
+    if (int rc = ensure_bounce(); rc != TSB_OK) return rc;
+    int i = 0;
+    for (size_t off = 0; off < bytes; off += kBounce, i++) {
       const size_t n = std::min(kBounce, bytes - off);
-      TSB_CUDA(cudaMemcpyAsync(bounce, static_cast<const uint8_t*>(src_d) + off, n, cudaMemcpyDeviceToHost, stream));
-      TSB_CUDA(cudaStreamSynchronize(stream));
-      std::memcpy(static_cast<uint8_t*>(dst_h) + off, bounce, n);
+      uint8_t* b = bounce + (i & 1) * kBounce;
+      if (i >= 2) TSB_CUDA(cudaEventSynchronize(bounce_ev[i & 1]));  // the DMA that last read this buffer is done
+      std::memcpy(b, static_cast<const uint8_t*>(src_h) + off, n);
+      TSB_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst_d) + off, b, n, cudaMemcpyHostToDevice, s));
+      TSB_CUDA(cudaEventRecord(bounce_ev[i & 1], s));
+    }
+    TSB_CUDA(cudaStreamSynchronize(s));
+    return TSB_OK;
+  }
+  int copy_d2h(void* dst_h, const void* src_d, size_t bytes, cudaStream_t s) {
+    if (!bytes) return TSB_OK;
+    if (reg.contains(dst_h, bytes)) {
+      TSB_CUDA(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, s));
+      TSB_CUDA(cudaStreamSynchronize(s));
+      return TSB_OK;
+    }
+    if (int rc = ensure_bounce(); rc != TSB_OK) return rc;
+    const size_t pieces = (bytes + kBounce - 1) / kBounce;
+    for (size_t i = 0; i <= pieces; i++) {  // DMA of piece i overlaps the host memcpy of piece i-1
+      if (i < pieces) {
+        const size_t off = i * kBounce, n = std::min(kBounce, bytes - off);
+        TSB_CUDA(cudaMemcpyAsync(bounce + (i & 1) * kBounce, static_cast<const uint8_t*>(src_d) + off, n,
+                                 cudaMemcpyDeviceToHost, s));
+        TSB_CUDA(cudaEventRecord(bounce_ev[i & 1], s));
+      }
+      if (i >= 1) {
+        const size_t off = (i - 1) * kBounce, n = std::min(kBounce, bytes - off);
+        TSB_CUDA(cudaEventSynchronize(bounce_ev[(i - 1) & 1]));
+        std::memcpy(static_cast<uint8_t*>(dst_h) + off, bounce + ((i - 1) & 1) * kBounce, n);
+      }
     }
     return TSB_OK;
   }
@@ -202,9 +232,10 @@ struct Base {
   template <class Launch>
   int evaluate_host(const void* in, int count, void* out, Launch&& launch) {
     const size_t in_b = in_rec * count, out_b = out_rec * count;
-    const bool in_locked = reg.ensure(in, in_b), out_locked = reg.ensure(out, out_b);
-    // AUTO: zero-copy whenever the caller's arrays could be page-locked and are 16-byte aligned (measured
-    // fastest at every chunk size, profiles/xfer_sweep_r1.txt); otherwise copies, pipelined when large
+    const bool in_locked = reg.contains(in, in_b), out_locked = reg.contains(out, out_b);
+    // AUTO: zero-copy whenever the caller registered its arrays (tsb_*_register_host) and they are 16-byte
+    // aligned (measured fastest at every chunk size, profiles/xfer_sweep_r1.txt); otherwise copies, pipelined
+    // when large, through the handle's pinned staging buffers for arrays that are not registered
     const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     const bool zc_ok = in_locked && out_locked && aligned && di.can_use_host_ptr;
     int mode = xfer == TSB_XFER_AUTO ? (zc_ok ? TSB_XFER_ZEROCOPY : TSB_XFER_MEMCPY) : xfer;
@@ -218,35 +249,33 @@ struct Base {
       TSB_CUDA(cudaStreamSynchronize(stream));
       return TSB_OK;
     }
-    const void* src = in;
-    void* dst = out;
+    const uint8_t* src = static_cast<const uint8_t*>(in);
+    uint8_t* dst = static_cast<uint8_t*>(out);
     if (!in_locked || !out_locked) {
       int rc = ensure_staging();
       if (rc != TSB_OK) return rc;
     }
-    if (!in_locked) {
-      std::memcpy(h_in, in, in_b);
-      src = h_in;
-    }
+    if (!in_locked) src = h_in;
     if (!out_locked) dst = h_out;
     if (count >= pipe_min && count > pipe_chunk) {
       // large chunk: sub-chunks alternate between two streams so that the upload of one overlaps the
-      // download of the previous one (PCIe is full duplex) and the kernel of the one in between
+      // download of the previous one (PCIe is full duplex) and the kernel of the one in between; the host
+      // memcpy into the staging buffer of sub-chunk i+1 overlaps the device work of sub-chunk i
       const cudaStream_t st[2] = {stream, stream2};
       int i = 0;
       for (int off = 0; off < count; off += pipe_chunk, ++i) {
         const int n = std::min(pipe_chunk, count - off);
         cudaStream_t s = st[i & 1];
-        TSB_CUDA(cudaMemcpyAsync(d_in + in_rec * off, static_cast<const uint8_t*>(src) + in_rec * off, in_rec * n,
-                                 cudaMemcpyHostToDevice, s));
+        if (!in_locked) std::memcpy(h_in + in_rec * off, static_cast<const uint8_t*>(in) + in_rec * off, in_rec * n);
+        TSB_CUDA(cudaMemcpyAsync(d_in + in_rec * off, src + in_rec * off, in_rec * n, cudaMemcpyHostToDevice, s));
         int rc = launch(d_in + in_rec * off, d_out + out_rec * off, n, s);
         if (rc != TSB_OK) return rc;
-        TSB_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + out_rec * off, d_out + out_rec * off, out_rec * n,
-                                 cudaMemcpyDeviceToHost, s));
+        TSB_CUDA(cudaMemcpyAsync(dst + out_rec * off, d_out + out_rec * off, out_rec * n, cudaMemcpyDeviceToHost, s));
       }
       TSB_CUDA(cudaStreamSynchronize(stream));
       TSB_CUDA(cudaStreamSynchronize(stream2));
     } else {
+      if (!in_locked) std::memcpy(h_in, in, in_b);
       TSB_CUDA(cudaMemcpyAsync(d_in, src, in_b, cudaMemcpyHostToDevice, stream));
       int rc = launch(d_in, d_out, count, stream);
       if (rc != TSB_OK) return rc;
@@ -426,11 +455,62 @@ struct DevicePool {
   }
 };
 
+// state of the persistent multi-round kernel of one handle (nq_rounds.cuh)
+struct RoundsCtx {
+  tsb::RoundsSync* d_sync = nullptr;
+  tsb::RoundsState* h_state = nullptr;  // pinned + mapped: written by the kernel when it leaves
+  tsb::RoundsState* d_state = nullptr;  // device alias of h_state
+  unsigned epoch = 0;
+  bool attr_set = false;
+  int threads = 256;  // CTA size (env TSB200_ROUNDS_THREADS = 256 | 512)
+  int ctas = 0;       // grid size (env TSB200_ROUNDS_CTAS; 0 = two CTAs per three SMs: an all-to-all flag exchange
+                      // among 148 CTAs costs 2-3x one among 74 (tools/flag_exchange.py), the per-CTA work grows
+                      // the other way; measured best around 100 CTAs of 256 threads)
+  unsigned long long* d_aux = nullptr;  // side word per arena position (nq_rounds.cuh)
+  long long aux_cap = 0, aux_valid = 0;
+  int ensure_aux(long long cap) {
+    if (cap <= aux_cap) return TSB_OK;
+    if (d_aux) cudaFree(d_aux);
+    d_aux = nullptr;
+    aux_cap = aux_valid = 0;
+    TSB_CUDA(cudaMalloc(&d_aux, static_cast<size_t>(cap) * sizeof(unsigned long long) + 256));
+    aux_cap = cap;
+    return TSB_OK;
+  }
+  int ensure(cudaStream_t s) {
+    if (const char* v = std::getenv("TSB200_ROUNDS_THREADS")) {
+      const int x = std::atoi(v);
+      if (x == 256 || x == 512) threads = x;
+    }
+    if (const char* v = std::getenv("TSB200_ROUNDS_CTAS")) ctas = std::max(1, std::atoi(v));
+    if (!d_sync) {
+      TSB_CUDA(cudaMalloc(&d_sync, sizeof(tsb::RoundsSync)));
+      TSB_CUDA(cudaMemsetAsync(d_sync, 0, sizeof(tsb::RoundsSync), s));
+    }
+    if (!h_state) {
+      TSB_CUDA(cudaHostAlloc(&h_state, sizeof(tsb::RoundsState), cudaHostAllocPortable | cudaHostAllocMapped));
+      TSB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_state), h_state, 0));
+    }
+    return TSB_OK;
+  }
+  void release() {
+    if (d_sync) cudaFree(d_sync);
+    if (h_state) cudaFreeHost(h_state);
+    if (d_aux) cudaFree(d_aux);
+    d_sync = nullptr;
+    h_state = d_state = nullptr;
+    d_aux = nullptr;
+    aux_cap = aux_valid = 0;
+  }
+};
+
 struct tsb_nq : Base {
   int N = 0, g = 1;
+  RoundsCtx rounds;
   int variant = 0;  // env TSB200_NQ_VARIANT (kernel A/B experiments)
-  int occ = 0;      // cached CTAs per SM
-  bool attr_set = false;
+  int tile_threads = 0;  // env TSB200_NQ_TILE_THREADS = 128 | 64: force the tile size (A/B experiments)
+  int occ[3] = {0, 0, 0};  // cached CTAs per SM, per tile size (128 / 64 / 32 threads)
+  bool attr_set[3] = {false, false, false};
   // fused expand (evaluate + generate_children on the device) and the device-resident pool
   ExpandCtx ex;
   uint8_t* d_children = nullptr;  // host-buffer expand: device image of the children
@@ -440,21 +520,34 @@ struct tsb_nq : Base {
 
 namespace {
 
-template <int N, int VAR>
-int launch_nq_n(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
-  auto kernel = tsb::nq_evaluate_kernel<N, VAR>;
-  const size_t smem = sizeof(tsb::NqSmem<N>) + 128;
-  if (!h->attr_set) {
+template <int N, int VAR, int T>
+int launch_nq_nt(tsb_nq* h, int slot, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
+  auto kernel = tsb::nq_evaluate_kernel<N, VAR, T>;
+  const size_t smem = sizeof(tsb::NqSmem<N, T>) + 128;
+  if (!h->attr_set[slot]) {
     TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    h->attr_set = true;
+    h->attr_set[slot] = true;
   }
   int grid = 1;
-  int rc = grid_for(kernel, tsb::NQ_THREADS, smem, count, tsb::NQ_TILE, h->di.sms, &grid, &h->occ);
+  int rc = grid_for(kernel, T, smem, count, T * tsb::NQ_QUAD, h->di.sms, &grid, &h->occ[slot]);
   if (rc != TSB_OK) return rc;
-  kernel<<<grid, tsb::NQ_THREADS, smem, s>>>(in, out, count);
+  kernel<<<grid, T, smem, s>>>(in, out, count);
   TSB_CUDA(cudaGetLastError());
   h->launches++;
   return TSB_OK;
+}
+// tile size by count: a chunk should make at least ~2 tiles per SM (at the reference's default --M 50000 tiles
+// of 512 parents would occupy 97 of the 148 SMs)
+template <int N, int VAR>
+int launch_nq_n(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
+  const long long want = 2LL * h->di.sms;
+  if (count / (128 * tsb::NQ_QUAD) >= want || h->tile_threads == 128) return launch_nq_nt<N, VAR, 128>(h, 0, in, out, count, s);
+  if constexpr (VAR == 0) {
+    if (count / (64 * tsb::NQ_QUAD) >= want || h->tile_threads == 64) return launch_nq_nt<N, VAR, 64>(h, 1, in, out, count, s);
+    return launch_nq_nt<N, VAR, 32>(h, 2, in, out, count, s);
+  } else {
+    return launch_nq_nt<N, VAR, 128>(h, 0, in, out, count, s);
+  }
 }
 
 int launch_nq(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
@@ -801,7 +894,7 @@ int pfsp_expand_round(tsb_pfsp* h, int lb_kind, const uint8_t* arena, const std:
   ++h->slow_rounds;
   long long n = 0;
   for (const PoolExtent& x : pieces) n += x.e - x.b;
-  if (n > h->M_max) return TSB_EINVAL;
+  if (n > h->M_max) return TSB_EINVAL;  // (cannot happen: every entry point checks count <= M_max first)
   long long at = 0;
   if (!(arena == h->d_in && pieces.size() == 1 && pieces[0].b == 0))
     for (const PoolExtent& x : pieces) {  // the chunk, contiguous
@@ -813,14 +906,14 @@ int pfsp_expand_round(tsb_pfsp* h, int lb_kind, const uint8_t* arena, const std:
   if (rc != TSB_OK) return rc;
   h->h_chunk.resize(static_cast<size_t>(n));
   h->h_bounds.resize(static_cast<size_t>(n) * h->jobs);
-  rc = h->copy_d2h(h->h_chunk.data(), h->d_in, static_cast<size_t>(n) * sizeof(tsb_pfsp_node));
-  if (rc == TSB_OK) rc = h->copy_d2h(h->h_bounds.data(), h->d_out, static_cast<size_t>(n) * h->jobs * 4);
+  rc = h->copy_d2h(h->h_chunk.data(), h->d_in, static_cast<size_t>(n) * sizeof(tsb_pfsp_node), s);
+  if (rc == TSB_OK) rc = h->copy_d2h(h->h_bounds.data(), h->d_out, static_cast<size_t>(n) * h->jobs * 4, s);
   if (rc != TSB_OK) return rc;
   h->h_kids.clear();
   uint64_t sol = 0;
   pfsp_generate_children_host(h->jobs, h->h_chunk.data(), static_cast<int>(n), h->h_bounds.data(), best, &h->h_kids,
                               &sol);
-  rc = h->copy_h2d(children_d, h->h_kids.data(), h->h_kids.size() * sizeof(tsb_pfsp_node));
+  rc = h->copy_h2d(children_d, h->h_kids.data(), h->h_kids.size() * sizeof(tsb_pfsp_node), s);
   if (rc != TSB_OK) return rc;
   *n_children = h->h_kids.size();
   *n_solutions = sol;
@@ -891,6 +984,7 @@ int tsb_nq_create(tsb_nq** out, int device, int N, int g, int M_max) {
   h->N = N;
   h->g = g;
   if (const char* v = std::getenv("TSB200_NQ_VARIANT")) h->variant = std::atoi(v);
+  if (const char* v = std::getenv("TSB200_NQ_TILE_THREADS")) h->tile_threads = std::atoi(v);
   int rc = h->init(device, M_max, sizeof(tsb_nq_node), static_cast<size_t>(N));
   if (rc != TSB_OK) {
     h->fini();
@@ -906,6 +1000,7 @@ void tsb_nq_destroy(tsb_nq* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->ex.release();
+  h->rounds.release();
   if (h->d_children) cudaFree(h->d_children);
   h->pool.release();
   h->fini();
@@ -945,7 +1040,7 @@ int tsb_nq_expand(tsb_nq* h, const void* parents, int count, void* children, uin
     TSB_CUDA(cudaMalloc(&h->d_children, need));
     h->d_children_bytes = need;
   }
-  int rc = h->copy_h2d(h->d_in, parents, sizeof(tsb_nq_node) * static_cast<size_t>(count));
+  int rc = h->copy_h2d(h->d_in, parents, sizeof(tsb_nq_node) * static_cast<size_t>(count), h->stream);
   if (rc != TSB_OK) return rc;
   unsigned long long nc = 0, ns = 0;
   const std::vector<PoolExtent> pieces{{0, count}};
@@ -954,7 +1049,7 @@ int tsb_nq_expand(tsb_nq* h, const void* parents, int count, void* children, uin
   *n_children = nc;
   *n_solutions = ns;
   if (nc > capacity) return TSB_ENOMEM;  // the caller's children array is too small; counts are valid
-  return h->copy_d2h(children, h->d_children, nc * sizeof(tsb_nq_node));
+  return h->copy_d2h(children, h->d_children, nc * sizeof(tsb_nq_node), h->stream);
 }
 
 namespace {
@@ -973,13 +1068,14 @@ int tsb_nq_pool_push(tsb_nq* h, const void* nodes, int64_t n) {
   if (!h || n < 0 || (n && !nodes)) return TSB_EINVAL;
   TSB_CUDA(cudaSetDevice(h->device));
   nq_pool_setup(h);
+  h->rounds.aux_valid = 0;  // (the side words of the persistent kernel describe the pool it left behind)
   int rc = h->pool.reserve(h->stream, n, nq_pool_min_cap(h));
   if (rc != TSB_OK) return rc;
   if (n == 0) return TSB_OK;
   const long long at = h->pool.top();
   // (on the handle's non-blocking stream, which the kernels of the next round are ordered after)
   rc = h->copy_h2d(h->pool.arena[h->pool.cur] + at * sizeof(tsb_nq_node), nodes,
-                   static_cast<size_t>(n) * sizeof(tsb_nq_node));
+                   static_cast<size_t>(n) * sizeof(tsb_nq_node), h->stream);
   if (rc != TSB_OK) return rc;
   if (h->pool.ext.empty())
     h->pool.ext.push_back({at, at + n});
@@ -998,6 +1094,7 @@ int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_ch
   DevicePool& p = h->pool;
   if (p.size < m) return TSB_OK;  // popBackBulk returns 0 below m (lib/commons/Pool.chpl:50-59)
   TSB_CUDA(cudaSetDevice(h->device));
+  h->rounds.aux_valid = 0;
   const long long n = std::min<long long>(p.size, M);
   // room above the top for the worst case (every slot of every parent survives); the chunk itself is read
   // in place, as the newest pieces of the extent stack
@@ -1025,6 +1122,169 @@ int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_ch
   return TSB_OK;
 }
 
+}  // extern "C"
+namespace {
+template <int N, int T>
+int nq_rounds_launch_nt(tsb_nq* h, const tsb::RoundsParams& prm, int grid, cudaStream_t s) {
+  auto kernel = tsb::nq_rounds_kernel<N, T>;
+  const size_t smem = sizeof(tsb::RoundsSmem<T>) + 128;
+  if (!h->rounds.attr_set) {
+    TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    h->rounds.attr_set = true;
+  }
+  void* args[] = {const_cast<tsb::RoundsParams*>(&prm)};
+  // cooperative: all CTAs co-resident (they exchange flags through L2), or the launch fails
+  TSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid), dim3(T), args, smem, s));
+  h->launches++;
+  return TSB_OK;
+}
+template <int N>
+int nq_rounds_launch_n(tsb_nq* h, const tsb::RoundsParams& prm, int grid, cudaStream_t s) {
+  if (h->rounds.threads == 256) return nq_rounds_launch_nt<N, 256>(h, prm, grid, s);
+  return nq_rounds_launch_nt<N, 512>(h, prm, grid, s);
+}
+int nq_rounds_launch(tsb_nq* h, const tsb::RoundsParams& prm, int grid, cudaStream_t s) {
+  switch (h->N) {
+#define TSB_NQ_CASE(n) \
+  case n:              \
+    return nq_rounds_launch_n<n>(h, prm, grid, s);
+    TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
+    TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
+    TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
+    TSB_NQ_CASE(20)
+#undef TSB_NQ_CASE
+  }
+  return TSB_EINVAL;
+}
+bool env_no_rounds() {
+  const char* v = std::getenv("TSB200_NO_ROUNDS");
+  return v && *v && *v != '0';
+}
+}  // namespace
+extern "C" {
+
+int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rounds, uint64_t* n_parents,
+                    uint64_t* n_children, uint64_t* n_solutions) {
+  if (!h || m < 1 || M < 1 || M > h->M_max || max_rounds < 0 || !n_rounds || !n_parents || !n_children || !n_solutions)
+    return TSB_EINVAL;
+  *n_rounds = *n_parents = *n_children = *n_solutions = 0;
+  DevicePool& p = h->pool;
+  TSB_CUDA(cudaSetDevice(h->device));
+  int rc = h->rounds.ensure(h->stream);
+  if (rc != TSB_OK) return rc;
+  int grid = std::min(h->di.sms, static_cast<int>(tsb::RND_MAX_CTAS));
+  grid = h->rounds.ctas > 0 ? std::min(grid, h->rounds.ctas) : std::max(1, 2 * grid / 3);
+  while (static_cast<long long>(grid) * h->rounds.threads * tsb::RND_PPT < M && grid < h->di.sms) ++grid;  // (M decides)
+  const bool persistent = static_cast<long long>(M) <= static_cast<long long>(grid) * h->rounds.threads * tsb::RND_PPT &&
+                          h->di.coop && !env_no_rounds();
+  if (!persistent) {  // large chunks: one round = two bandwidth-bound kernels (tsb_nq_pool_step)
+    while (static_cast<int64_t>(*n_rounds) < max_rounds) {
+      int64_t np = 0;
+      uint64_t nc = 0, ns = 0;
+      int rc = tsb_nq_pool_step(h, m, M, &np, &nc, &ns);
+      if (rc != TSB_OK) return rc;
+      if (np == 0) break;
+      ++*n_rounds;
+      *n_parents += static_cast<uint64_t>(np);
+      *n_children += nc;
+      *n_solutions += ns;
+    }
+    return TSB_OK;
+  }
+  nq_pool_setup(h);
+  while (p.size >= m && static_cast<int64_t>(*n_rounds) < max_rounds) {
+    // the kernel works on ONE contiguous stack [0, size) with room for the worst case of the next round
+    const long long n = std::min<long long>(p.size, M);
+    const long long need = p.size - n + n * h->N;
+    if (need > p.cap) {
+      rc = p.compact(h->stream, std::max<long long>(2 * p.cap, need + need / 2));
+      h->rounds.aux_valid = 0;
+    } else if (p.ext.size() != 1 || p.ext[0].b != 0) {
+      rc = p.compact(h->stream, p.cap);
+      h->rounds.aux_valid = 0;
+    }
+    if (rc == TSB_OK) rc = h->rounds.ensure_aux(p.cap);
+    if (rc != TSB_OK) return rc;
+    tsb::RoundsParams prm;
+    prm.aux = h->rounds.d_aux;
+    prm.aux_valid = std::min(h->rounds.aux_valid, p.size);
+    prm.arena = p.arena[p.cur];
+    prm.cap = p.cap;
+    prm.size0 = p.size;
+    prm.epoch0 = h->rounds.epoch;
+    prm.m = m;
+    prm.M = M;
+    prm.max_rounds = max_rounds - static_cast<int64_t>(*n_rounds);
+    prm.prof = std::getenv("TSB200_ROUNDS_PROF") != nullptr;
+    prm.sync = h->rounds.d_sync;
+    prm.state = h->rounds.d_state;
+    h->rounds.h_state->exit_code = -1;
+    rc = nq_rounds_launch(h, prm, grid, h->stream);
+    if (rc != TSB_OK) return rc;
+    TSB_CUDA(cudaStreamSynchronize(h->stream));
+    const tsb::RoundsState st = *h->rounds.h_state;
+    if (st.exit_code < 0 || st.exit_code == tsb::RND_EXIT_ABORT) {
+      g_last_cuda_error = "nq_rounds_kernel: watchdog abort (a flag exchange did not complete)";
+      return TSB_ECUDA;
+    }
+    if (prm.prof)
+      std::fprintf(stderr, "[tsb200] rounds kernel: %llu rounds; CTA 0 cycles per round: wait-done %.0f load %.0f eval+scan %.0f "
+                   "gather %.0f build+store %.0f release %.0f\n", static_cast<unsigned long long>(st.rounds),
+                   1.0 * st.prof[0] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[1] / std::max<unsigned long long>(1, st.rounds),
+                   1.0 * st.prof[2] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[3] / std::max<unsigned long long>(1, st.rounds),
+                   1.0 * st.prof[4] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[5] / std::max<unsigned long long>(1, st.rounds));
+    h->rounds.epoch = st.epoch;
+    h->rounds.aux_valid = st.size;
+    p.size = st.size;
+    p.ext.clear();
+    if (p.size) p.ext.push_back({0, p.size});
+    *n_rounds += st.rounds;
+    *n_parents += st.parents;
+    *n_children += st.children;
+    *n_solutions += st.solutions;
+    if (st.exit_code == tsb::RND_EXIT_SPACE && st.rounds == 0 && need <= p.cap) return TSB_ENOMEM;  // (cannot happen)
+    if (st.exit_code != tsb::RND_EXIT_SPACE) break;  // DONE or PAUSE
+  }
+  return TSB_OK;
+}
+
+// diagnostics: cycles per round of the bare flag-exchange skeleton of the persistent kernel (nq_rounds.cuh)
+int tsb_debug_flag_exchange(int device, int rounds, int variant, int ctas, double* cycles_per_round) {
+  if (!cycles_per_round || rounds < 1) return TSB_EINVAL;
+  DeviceInfo di;
+  int rc = query_device(device, di);
+  if (rc != TSB_OK) return rc;
+  if (!di.coop) return TSB_EUNSUPPORTED;
+  tsb::RoundsSync* sy = nullptr;
+  uint4* scratch = nullptr;
+  long long* d_out = nullptr;
+  int grid = std::min(di.sms, static_cast<int>(tsb::RND_MAX_CTAS));
+  if (ctas > 0 && ctas < grid) grid = ctas;
+  TSB_CUDA(cudaMalloc(&sy, sizeof(*sy)));
+  const size_t scratch_bytes = std::max<size_t>((static_cast<size_t>(grid) * tsb::RND_THREADS + 2) * sizeof(uint4), 2 * 256 * 256 * 4);
+  TSB_CUDA(cudaMalloc(&scratch, scratch_bytes));
+  TSB_CUDA(cudaMemset(scratch, 0, scratch_bytes));
+  TSB_CUDA(cudaMalloc(&d_out, sizeof(long long)));
+  TSB_CUDA(cudaMemset(sy, 0, sizeof(*sy)));
+  unsigned epoch0 = 0;
+  void* args[] = {&sy, &epoch0, &rounds, &variant, &scratch, &d_out};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tsb::rounds_sync_bench_kernel), dim3(grid),
+                                              dim3(tsb::RND_THREADS), args, 0, nullptr);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  long long cyc = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
+  cudaFree(sy);
+  cudaFree(scratch);
+  cudaFree(d_out);
+  if (e != cudaSuccess) {
+    g_last_cuda_error = std::string("flag exchange bench: ") + cudaGetErrorString(e);
+    (void)cudaGetLastError();
+    return TSB_ECUDA;
+  }
+  *cycles_per_round = static_cast<double>(cyc) / rounds;
+  return TSB_OK;
+}
+
 int tsb_nq_pool_drain(tsb_nq* h, void* nodes, int64_t capacity, int64_t* n) {
   if (!h || !n || capacity < 0) return TSB_EINVAL;
   DevicePool& p = h->pool;
@@ -1035,7 +1295,7 @@ int tsb_nq_pool_drain(tsb_nq* h, void* nodes, int64_t capacity, int64_t* n) {
   for (const PoolExtent& x : p.ext) {  // extents are the pool in logical (oldest first) order
     int rc = h->copy_d2h(static_cast<uint8_t*>(nodes) + at * sizeof(tsb_nq_node),
                          p.arena[p.cur] + x.b * sizeof(tsb_nq_node),
-                         static_cast<size_t>(x.e - x.b) * sizeof(tsb_nq_node));
+                         static_cast<size_t>(x.e - x.b) * sizeof(tsb_nq_node), h->stream);
     if (rc != TSB_OK) return rc;
     at += x.e - x.b;
   }
@@ -1062,6 +1322,17 @@ int tsb_nq_evaluate_device(tsb_nq* h, const void* parents_d, int count, uint8_t*
   TSB_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   return launch_nq(h, static_cast<const uint8_t*>(parents_d), labels_d, count, s);
+}
+
+int tsb_nq_register_host(tsb_nq* h, void* ptr, size_t bytes) {
+  if (!h) return TSB_EINVAL;
+  TSB_CUDA(cudaSetDevice(h->device));
+  return h->reg.add(ptr, bytes);
+}
+int tsb_nq_unregister_host(tsb_nq* h, void* ptr) {
+  if (!h) return TSB_EINVAL;
+  TSB_CUDA(cudaSetDevice(h->device));
+  return h->reg.remove(ptr);
 }
 
 int tsb_nq_set_xfer(tsb_nq* h, int mode) {
@@ -1235,6 +1506,17 @@ int tsb_pfsp_evaluate_device(tsb_pfsp* h, int lb_kind, const void* parents_d, in
                      count, best, s);
 }
 
+int tsb_pfsp_register_host(tsb_pfsp* h, void* ptr, size_t bytes) {
+  if (!h) return TSB_EINVAL;
+  TSB_CUDA(cudaSetDevice(h->device));
+  return h->reg.add(ptr, bytes);
+}
+int tsb_pfsp_unregister_host(tsb_pfsp* h, void* ptr) {
+  if (!h) return TSB_EINVAL;
+  TSB_CUDA(cudaSetDevice(h->device));
+  return h->reg.remove(ptr);
+}
+
 int tsb_pfsp_set_xfer(tsb_pfsp* h, int mode) {
   if (!h || mode < 0 || mode > 2) return TSB_EINVAL;
   h->xfer = mode;
@@ -1280,7 +1562,7 @@ int tsb_pfsp_expand(tsb_pfsp* h, int lb_kind, const void* parents, int count, in
     TSB_CUDA(cudaMalloc(&h->d_children, need));
     h->d_children_bytes = need;
   }
-  int rc = h->copy_h2d(h->d_in, parents, sizeof(tsb_pfsp_node) * static_cast<size_t>(count));
+  int rc = h->copy_h2d(h->d_in, parents, sizeof(tsb_pfsp_node) * static_cast<size_t>(count), h->stream);
   if (rc != TSB_OK) return rc;
   unsigned long long nc = 0, ns = 0;
   const std::vector<PoolExtent> pieces{{0, count}};
@@ -1289,7 +1571,7 @@ int tsb_pfsp_expand(tsb_pfsp* h, int lb_kind, const void* parents, int count, in
   *n_children = nc;
   *n_solutions = ns;
   if (nc > capacity) return TSB_ENOMEM;
-  return h->copy_d2h(children, h->d_children, nc * sizeof(tsb_pfsp_node));
+  return h->copy_d2h(children, h->d_children, nc * sizeof(tsb_pfsp_node), h->stream);
 }
 
 int tsb_pfsp_pool_push(tsb_pfsp* h, const void* nodes, int64_t n) {
@@ -1301,7 +1583,7 @@ int tsb_pfsp_pool_push(tsb_pfsp* h, const void* nodes, int64_t n) {
   if (n == 0) return TSB_OK;
   const long long at = h->pool.top();
   rc = h->copy_h2d(h->pool.arena[h->pool.cur] + at * sizeof(tsb_pfsp_node), nodes,
-                   static_cast<size_t>(n) * sizeof(tsb_pfsp_node));
+                   static_cast<size_t>(n) * sizeof(tsb_pfsp_node), h->stream);
   if (rc != TSB_OK) return rc;
   if (h->pool.ext.empty())
     h->pool.ext.push_back({at, at + n});
@@ -1359,7 +1641,7 @@ int tsb_pfsp_pool_drain(tsb_pfsp* h, void* nodes, int64_t capacity, int64_t* n) 
   for (const PoolExtent& x : p.ext) {
     int rc = h->copy_d2h(static_cast<uint8_t*>(nodes) + at * sizeof(tsb_pfsp_node),
                          p.arena[p.cur] + x.b * sizeof(tsb_pfsp_node),
-                         static_cast<size_t>(x.e - x.b) * sizeof(tsb_pfsp_node));
+                         static_cast<size_t>(x.e - x.b) * sizeof(tsb_pfsp_node), h->stream);
     if (rc != TSB_OK) return rc;
     at += x.e - x.b;
   }

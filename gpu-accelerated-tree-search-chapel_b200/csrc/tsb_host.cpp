@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <climits>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -144,6 +145,9 @@ void nq_gpu_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool
   if (r.rc != TSB_OK) return;
   std::vector<tsb_nq_node> parents(M);
   std::vector<uint8_t> labels(static_cast<size_t>(M) * N);
+  // the chunk arrays live for the whole step 2 (nqueens_gpu_chpl.chpl:191-192): page-lock them once
+  tsb_nq_register_host(h, parents.data(), parents.size() * sizeof(tsb_nq_node));
+  tsb_nq_register_host(h, labels.data(), labels.size());
   for (;;) {
     const int n = pool.popBackBulk(m, M, parents.data());
     if (n <= 0) break;
@@ -172,18 +176,13 @@ void nq_devpool_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& 
                           (tt1 - tt0) * 1e3, (tt2 - tt1) * 1e3);
   pool.front = 0;
   pool.size = 0;
-  while (r.rc == TSB_OK) {
-    int64_t np = 0;
-    uint64_t nc = 0, ns = 0;
-    r.rc = tsb_nq_pool_step(h, m, M, &np, &nc, &ns);
-    if (r.rc != TSB_OK || np == 0) break;
+  if (r.rc == TSB_OK) {  // all rounds of step 2 (one persistent kernel for small M, two kernels per round otherwise)
+    uint64_t nr = 0, np = 0, nc = 0, ns = 0;
+    r.rc = tsb_nq_pool_run(h, m, M, INT64_MAX, &nr, &np, &nc, &ns);
     r.tree += nc;
     r.sol += ns;
-    ++r.offloads;
-    r.parents += static_cast<uint64_t>(np);
-    if (trace && (r.offloads == 1 || r.offloads == 10 || r.offloads == 100 || r.offloads == 1000))
-      std::fprintf(stderr, "[tsb200] device %d: %llu rounds after %.1f ms\n", device,
-                   static_cast<unsigned long long>(r.offloads), (now_s() - tt2) * 1e3);
+    r.offloads += nr;
+    r.parents += np;
   }
   if (trace) std::fprintf(stderr, "[tsb200] device %d: %llu rounds in %.1f ms\n", device,
                           static_cast<unsigned long long>(r.offloads), (now_s() - tt2) * 1e3);
@@ -356,6 +355,9 @@ void pfsp_gpu_task(int device, const tsb_pfsp_tables& t, int lb_kind, int m, int
   const int jobs = t.jobs;
   std::vector<tsb_pfsp_node> parents(M);
   std::vector<int32_t> bounds(static_cast<size_t>(M) * jobs);
+  // the chunk arrays live for the whole step 2 (pfsp_gpu_chpl.chpl:355-356): page-lock them once
+  tsb_pfsp_register_host(h, parents.data(), parents.size() * sizeof(tsb_pfsp_node));
+  tsb_pfsp_register_host(h, bounds.data(), bounds.size() * sizeof(int32_t));
   for (;;) {
     const int n = pool.popBackBulk(m, M, parents.data());
     if (n <= 0) break;

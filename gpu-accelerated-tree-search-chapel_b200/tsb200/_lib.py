@@ -67,6 +67,10 @@ SYMBOLS = {
     "tsb_nq_pool_size": (_i64, [_vp]),
     "tsb_nq_pool_step": (_i, [_vp, _i, _i, C.POINTER(_i64), C.POINTER(_u64), C.POINTER(_u64)]),
     "tsb_nq_pool_drain": (_i, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    "tsb_nq_pool_run": (_i, [_vp, _i, _i, _i64, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "tsb_nq_register_host": (_i, [_vp, _vp, C.c_size_t]),
+    "tsb_nq_unregister_host": (_i, [_vp, _vp]),
+    "tsb_debug_flag_exchange": (_i, [_i, _i, _i, _i, C.POINTER(C.c_double)]),
     "tsb_nq_set_xfer": (_i, [_vp, _i]),
     "tsb_nq_kernel_launches": (_u64, [_vp]),
     "tsb_pfsp_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _pi32, _pi32, _pi32, _i, _pi32, _pi32, _pi32, _pi32, _pi32]),
@@ -80,6 +84,8 @@ SYMBOLS = {
     "tsb_pfsp_pool_step": (_i, [_vp, _i, _i, _i, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_u64), C.POINTER(_u64)]),
     "tsb_pfsp_pool_drain": (_i, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "tsb_pfsp_slow_rounds": (_u64, [_vp]),
+    "tsb_pfsp_register_host": (_i, [_vp, _vp, C.c_size_t]),
+    "tsb_pfsp_unregister_host": (_i, [_vp, _vp]),
     "tsb_pfsp_set_xfer": (_i, [_vp, _i]),
     "tsb_pfsp_kernel_launches": (_u64, [_vp]),
     "tsb_taillard_nb_jobs": (_i, [_i]),

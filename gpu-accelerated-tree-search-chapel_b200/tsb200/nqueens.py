@@ -36,6 +36,14 @@ class NQueensEvaluator:
     def set_xfer(self, mode: int):
         check(lib().tsb_nq_set_xfer(self._h, mode), "tsb_nq_set_xfer")
 
+    def register_host(self, arr: np.ndarray) -> None:
+        """page-lock + map a long-lived host array (the driver's `parents` / `labels`, allocated once per search)
+        so that evaluate_gpu works on it in place; the array must outlive the evaluator or be unregistered"""
+        check(lib().tsb_nq_register_host(self._h, arr.ctypes.data, arr.nbytes), "tsb_nq_register_host")
+
+    def unregister_host(self, arr: np.ndarray) -> None:
+        check(lib().tsb_nq_unregister_host(self._h, arr.ctypes.data), "tsb_nq_unregister_host")
+
     @property
     def kernel_launches(self) -> int:
         return int(lib().tsb_nq_kernel_launches(self._h))
@@ -87,6 +95,14 @@ class NQueensEvaluator:
         np_, nc, ns = C.c_int64(0), C.c_uint64(0), C.c_uint64(0)
         check(lib().tsb_nq_pool_step(self._h, m, M, C.byref(np_), C.byref(nc), C.byref(ns)), "tsb_nq_pool_step")
         return int(np_.value), int(nc.value), int(ns.value)
+
+    def pool_run(self, m: int, M: int, max_rounds: int = 2**62):
+        """(rounds, parents popped, children appended, solutions) of up to max_rounds device-side offload rounds
+        (until the pool holds fewer than m nodes); one persistent kernel for M <= 512 x #SMs"""
+        nr, np_, nc, ns = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(lib().tsb_nq_pool_run(self._h, m, M, max_rounds, C.byref(nr), C.byref(np_), C.byref(nc), C.byref(ns)),
+              "tsb_nq_pool_run")
+        return int(nr.value), int(np_.value), int(nc.value), int(ns.value)
 
     def pool_drain(self) -> np.ndarray:
         n = self.pool_size

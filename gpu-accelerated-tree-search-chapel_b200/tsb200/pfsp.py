@@ -46,6 +46,13 @@ class PfspEvaluator:
     def set_xfer(self, mode: int):
         check(lib().tsb_pfsp_set_xfer(self._h, mode), "tsb_pfsp_set_xfer")
 
+    def register_host(self, arr: np.ndarray) -> None:
+        """page-lock + map a long-lived host array (the driver's `parents` / `bounds`); see NQueensEvaluator"""
+        check(lib().tsb_pfsp_register_host(self._h, arr.ctypes.data, arr.nbytes), "tsb_pfsp_register_host")
+
+    def unregister_host(self, arr: np.ndarray) -> None:
+        check(lib().tsb_pfsp_unregister_host(self._h, arr.ctypes.data), "tsb_pfsp_unregister_host")
+
     @property
     def kernel_launches(self) -> int:
         return int(lib().tsb_pfsp_kernel_launches(self._h))

@@ -9,8 +9,13 @@
  *
  * One handle per (task, device); distinct handles are fully concurrent, a handle is not
  * re-entrant.  The library owns all device and pinned staging memory; caller pointers are
- * never retained past return, except that host ranges may stay page-locked (cudaHostRegister)
- * between calls for speed (disable with env TSB200_NO_REGISTER=1) — tsb_*_destroy() releases them.
+ * never retained past return.  A caller that keeps its chunk arrays for the whole search (the
+ * Chapel drivers allocate `parents` / `labels` once, nqueens_gpu_chpl.chpl:191-192) may hand them
+ * to tsb_*_register_host(): the range is page-locked + mapped (cudaHostRegister) and
+ * tsb_*_evaluate then works on it in place (zero-copy over PCIe).  Registration is explicit and
+ * the caller owns the lifetime: a registered array must stay allocated until it is unregistered
+ * or the handle is destroyed.  Arrays that were never registered go through the handle's pinned
+ * staging buffers.  (env TSB200_NO_REGISTER=1 turns registration into a no-op.)
  *
  * Node wire formats (must match the Chapel records bit for bit):
  *   N-Queens  lib/nqueens/NQueens_node.chpl:9-11   { uint8 depth; uint8 board[20]; }   21 B, align 1
@@ -121,9 +126,25 @@ int tsb_nq_pool_push(tsb_nq* h, const void* nodes, int64_t n);
 int64_t tsb_nq_pool_size(const tsb_nq* h);
 int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_children, uint64_t* n_solutions);
 int tsb_nq_pool_drain(tsb_nq* h, void* nodes, int64_t capacity_nodes, int64_t* n);
+/* rounds until the pool holds fewer than m nodes (or max_rounds are done): exactly the sequence of
+ * tsb_nq_pool_step rounds — the same chunks, the same pool after every round — but for chunk sizes up to
+ * 512 x #SMs (the reference's default --M 50000) the whole loop of nqueens_gpu_chpl.chpl:197-215 runs inside ONE
+ * persistent cooperative kernel (two flag exchanges through L2 per round instead of two launches and a host
+ * round trip); larger M falls back to one tsb_nq_pool_step per round.  Totals over the rounds come back. */
+int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rounds, uint64_t* n_parents,
+                    uint64_t* n_children, uint64_t* n_solutions);
 
+/* page-lock + map a caller-owned host array for the lifetime of the handle (see the header comment);
+ * TSB_EINVAL if the range partly overlaps a registered one / was not registered */
+int tsb_nq_register_host(tsb_nq* h, void* ptr, size_t bytes);
+int tsb_nq_unregister_host(tsb_nq* h, void* ptr);
 int tsb_nq_set_xfer(tsb_nq* h, int mode);
 uint64_t tsb_nq_kernel_launches(const tsb_nq* h); /* kernels launched through this handle so far */
+
+/* diagnostics: SM cycles per round of the bare two-flag-exchange skeleton of the persistent multi-round kernel
+ * (no evaluation, no children) — the floor under a round of tsb_nq_pool_run; variant bits: 1 = no release fence,
+ * 2 = no acquire fence, 4 = 16 bytes per thread stored before the release, 8 = weak L2 polls, 16 = one exchange */
+int tsb_debug_flag_exchange(int device, int rounds, int variant, int ctas /* 0 = one per SM */, double* cycles_per_round);
 
 /* ------------------------------------------------------------------ PFSP ----------------- */
 typedef struct tsb_pfsp tsb_pfsp;
@@ -169,6 +190,8 @@ int64_t tsb_pfsp_pool_size(const tsb_pfsp* h);
 int tsb_pfsp_pool_step(tsb_pfsp* h, int lb_kind, int m, int M, int64_t* best, int64_t* n_parents,
                        uint64_t* n_children, uint64_t* n_solutions);
 int tsb_pfsp_pool_drain(tsb_pfsp* h, void* nodes, int64_t capacity_nodes, int64_t* n);
+int tsb_pfsp_register_host(tsb_pfsp* h, void* ptr, size_t bytes);
+int tsb_pfsp_unregister_host(tsb_pfsp* h, void* ptr);
 int tsb_pfsp_set_xfer(tsb_pfsp* h, int mode);
 uint64_t tsb_pfsp_kernel_launches(const tsb_pfsp* h);
 uint64_t tsb_pfsp_slow_rounds(const tsb_pfsp* h); /* expand rounds redone on the host because a leaf improved best */

@@ -92,4 +92,71 @@ def test_device_resident_search_counts(golden_dir, N, m, M, D):
     assert (st.explored_tree, st.explored_sol) == (counts["tree"], counts["sol"])
     ref = po.nq_search_offload(N, 1, m, M, D)  # same chunk sequence as the reference driver
     assert (st.offloads, st.offloaded_parents) == (ref.offloads, ref.offloaded_parents)
-    assert st.kernel_launches == 2 * st.offloads  # count, build
+    if M <= 512 * 100:  # the persistent multi-round kernel: a handful of launches for all rounds
+        assert 0 < st.kernel_launches < max(16, st.offloads // 4 + 16)
+    else:
+        assert st.kernel_launches == 2 * st.offloads  # count, build
+
+
+@pytest.mark.parametrize("N,m,M,rounds", [(11, 25, 700, 40), (12, 5, 300, 200), (13, 25, 5000, 37), (14, 25, 50000, 11),
+                                          (17, 25, 50000, 6), (10, 1, 75000, 50), (8, 25, 50000, 1000)])
+def test_pool_run_equals_the_same_number_of_pool_steps(N, m, M, rounds):
+    """tsb_nq_pool_run (persistent cooperative kernel, children stored in place) against tsb_nq_pool_step (two
+    kernels per round, extent stack): same counters, byte-identical pool, round by round and in bulk; and against
+    the oracle's sequential rule"""
+    rng = np.random.default_rng(N * 1000 + M)
+    start = rand_nq(rng, N, 60, depth_lo=1, depth_hi=2)
+    with tsb200.NQueensEvaluator(N, M=M) as a, tsb200.NQueensEvaluator(N, M=M) as b:
+        a.pool_push(start)
+        b.pool_push(start)
+        tot = [0, 0, 0, 0]
+        done = 0
+        for _ in range(rounds):
+            n_par, n_child, n_sol = a.pool_step(m, M)
+            if n_par == 0:
+                break
+            done += 1
+            tot = [tot[0] + 1, tot[1] + n_par, tot[2] + n_child, tot[3] + n_sol]
+        # the same rounds in three launches of the persistent kernel: 1 round, a few, the rest
+        got = [0, 0, 0, 0]
+        for k in (1, 3, rounds):
+            r = b.pool_run(m, M, min(k, rounds - got[0]))
+            got = [x + y for x, y in zip(got, r)]
+        assert got == tot and a.pool_size == b.pool_size
+        ra, rb = a.pool_drain(), b.pool_drain()
+        assert ra.tobytes() == rb.tobytes()
+        assert b.kernel_launches <= 3
+
+
+def test_pool_run_against_the_oracle_rule_and_growth(monkeypatch):
+    """a tiny arena (TSB200_POOL_CAP) makes the persistent kernel leave for more room several times"""
+    monkeypatch.setenv("TSB200_POOL_CAP", "2000")
+    N, m, M = 11, 25, 700
+    rng = np.random.default_rng(44)
+    start = rand_nq(rng, N, 60, depth_lo=1, depth_hi=3)
+    host_pool = start.copy()
+    tot = [0, 0, 0, 0]
+    for _ in range(25):
+        if host_pool.shape[0] < m:
+            break
+        n = min(host_pool.shape[0], M)
+        chunk = np.ascontiguousarray(host_pool[host_pool.shape[0] - n:])
+        kids, sol = po.nq_expand(chunk.view(po.NQ_NODE_DTYPE), N)
+        host_pool = np.concatenate([host_pool[: host_pool.shape[0] - n], kids.view(tsb200.NQ_NODE_DTYPE)])
+        tot = [tot[0] + 1, tot[1] + n, tot[2] + kids.shape[0], tot[3] + sol]
+    with tsb200.NQueensEvaluator(N, M=M) as ev:
+        ev.pool_push(start)
+        assert list(ev.pool_run(m, M, 25)) == tot
+        assert ev.pool_drain().tobytes() == np.ascontiguousarray(host_pool).tobytes()
+
+
+def test_pool_run_to_exhaustion_counts(golden_dir):
+    """the whole step 2 of N = 13 in one call, m = 1: the pool runs empty; children + 1 root = explored tree"""
+    N = 13
+    counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
+    root = np.zeros(1, dtype=tsb200.NQ_NODE_DTYPE)
+    root["board"][0, :N] = np.arange(N)
+    with tsb200.NQueensEvaluator(N, M=50000) as ev:
+        ev.pool_push(root)
+        nr, npar, nc, ns = ev.pool_run(1, 50000)
+        assert (nc, ns) == (counts["tree"], counts["sol"]) and npar == nc + 1 and ev.pool_size == 0

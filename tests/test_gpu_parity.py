@@ -112,21 +112,63 @@ def test_nq_edge_cases():
         check_nq(ev, view, N)
 
 
-@pytest.mark.parametrize("mode", [tsb200.XFER_MEMCPY, tsb200.XFER_ZEROCOPY])
-def test_nq_transfer_modes(mode, monkeypatch):
-    N = 17
+@pytest.mark.parametrize("mode", [tsb200.XFER_AUTO, tsb200.XFER_MEMCPY, tsb200.XFER_ZEROCOPY])
+@pytest.mark.parametrize("registered", [False, True])
+def test_nq_transfer_modes(mode, registered):
+    """driver-style use: `parents` / `labels` allocated once, optionally page-locked with register_host (then
+    AUTO / ZEROCOPY run the kernel directly on them over PCIe); unregistered arrays take the staging path"""
+    N, M = 17, 300000  # > the two-stream pipelining threshold of the copy path
     rng = np.random.default_rng(77)
-    with tsb200.NQueensEvaluator(N, M=50000) as ev:
+    with tsb200.NQueensEvaluator(N, M=M) as ev:
         ev.set_xfer(mode)
-        for count in (50000, 1234, 50000, 7):
-            check_nq(ev, rand_nq(rng, N, count), N)
+        parents = np.zeros(M, dtype=tsb200.NQ_NODE_DTYPE)
+        labels = np.empty(M * N, dtype=np.uint8)
+        if registered:
+            ev.register_host(parents)
+            ev.register_host(labels)
+            ev.register_host(labels)  # registering a registered range again is a no-op
+        for count in (50000, 1234, M, 7):
+            parents[:count] = rand_nq(rng, N, count)
+            labels[:] = 7
+            ev.evaluate_gpu(parents, count * N, labels)
+            want = po.nq_evaluate(parents[:count].view(po.NQ_NODE_DTYPE), N).reshape(-1, N)
+            live = po.nq_live_mask(parents[:count].view(po.NQ_NODE_DTYPE), N)
+            np.testing.assert_array_equal(labels[: count * N].reshape(-1, N)[live], want[live])
+        if registered:
+            ev.unregister_host(parents)
+            ev.unregister_host(labels)
+            with pytest.raises(tsb200.TsbError):
+                ev.unregister_host(labels)  # not registered any more
+
+
+def test_nq_fresh_arrays_every_call_never_stale():
+    """regression: nothing stays page-locked behind the caller's back, so arrays that are freed and
+    re-allocated at the same addresses between calls are always read / written through the current mapping"""
+    N = 17
+    rng = np.random.default_rng(78)
+    with tsb200.NQueensEvaluator(N, M=400000) as ev:
+        for it in range(6):
+            count = 400000 if it % 2 == 0 else 300000
+            parents = rand_nq(rng, N, count)       # fresh (large: mmap'ed) arrays each iteration, freed after
+            check_nq(ev, parents, N)               # ev.evaluate allocates a fresh labels array as well
+            del parents
+        # explicit registration with caller-owned lifetime: unregister before the array goes away
+        parents = rand_nq(rng, N, 400000)
+        ev.register_host(parents)
+        check_nq(ev, parents, N)
+        ev.unregister_host(parents)
+        del parents
+        check_nq(ev, rand_nq(rng, N, 400000), N)
 
 
 def test_nq_without_host_registration(monkeypatch):
-    monkeypatch.setenv("TSB200_NO_REGISTER", "1")
+    monkeypatch.setenv("TSB200_NO_REGISTER", "1")  # register_host becomes a no-op
     N = 14
     with tsb200.NQueensEvaluator(N, M=20000) as ev:
-        check_nq(ev, rand_nq(np.random.default_rng(3), N, 20000), N)
+        parents = rand_nq(np.random.default_rng(3), N, 20000)
+        ev.register_host(parents)
+        check_nq(ev, parents, N)
+        ev.unregister_host(parents)
 
 
 @pytest.mark.parametrize("N,which", [(12, 3), (14, 100), (15, 40)])
@@ -254,10 +296,15 @@ def test_pfsp_root_uses_min_heads():
 @pytest.mark.parametrize("lb,which", [("lb1", 30), ("lb1_d", 30), ("lb2", 10)])
 def test_pfsp_captured_real_chunks(lb, which):
     parents, best = po.pfsp_capture_chunk(14, tsb200.LB_NAMES[lb], which)
+    parents = np.ascontiguousarray(parents.view(tsb200.PFSP_NODE_DTYPE))
     with tsb200.PfspEvaluator(14, M=50000) as ev:
-        for mode in (tsb200.XFER_MEMCPY, tsb200.XFER_ZEROCOPY):
-            ev.set_xfer(mode)
-            check_pfsp(ev, parents.view(tsb200.PFSP_NODE_DTYPE), lb, best)
+        for registered in (False, True):
+            if registered:
+                ev.register_host(parents)
+            for mode in (tsb200.XFER_MEMCPY, tsb200.XFER_ZEROCOPY):
+                ev.set_xfer(mode)
+                check_pfsp(ev, parents, lb, best)
+        ev.unregister_host(parents)
 
 
 @pytest.mark.parametrize("lb,D", [("lb1", 1), ("lb1_d", 1), ("lb2", 1), ("lb1", 4), ("lb2", 2)])
