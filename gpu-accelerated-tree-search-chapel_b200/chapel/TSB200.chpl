@@ -58,6 +58,8 @@ module TSB200 {
   extern proc tsb_nq_pool_size(h: c_ptr(tsb_nq)): int(64);
   extern proc tsb_nq_pool_step(h: c_ptr(tsb_nq), m: c_int, M: c_int, ref n_parents: int(64),
                                ref n_children: uint(64), ref n_solutions: uint(64)): c_int;
+  extern proc tsb_nq_pool_steal(victim: c_ptr(tsb_nq), thief: c_ptr(tsb_nq), m: c_int, ref n_stolen: int(64)): c_int;
+  extern proc tsb_pfsp_pool_steal(victim: c_ptr(tsb_pfsp), thief: c_ptr(tsb_pfsp), m: c_int, ref n_stolen: int(64)): c_int;
   extern proc tsb_nq_pool_run(h: c_ptr(tsb_nq), m: c_int, M: c_int, max_rounds: int(64), ref n_rounds: uint(64),
                               ref n_parents: uint(64), ref n_children: uint(64), ref n_solutions: uint(64)): c_int;
   extern proc tsb_nq_pool_drain(h: c_ptr(tsb_nq), nodes: c_ptr(void), capacity_nodes: int(64),

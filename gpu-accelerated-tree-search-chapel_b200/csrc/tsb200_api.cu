@@ -682,6 +682,61 @@ void pool_pop(DevicePool& p, long long n) {
 
 }  // namespace
 
+namespace {
+// Work stealing between device pools (the reference steals between its per-GPU host pools,
+// nqueens_multigpu_chpl.chpl:255-312): the OLDEST half of the victim's pool (popFrontBulkFree,
+// lib/commons/Pool_par.chpl:178-191: size / 2 nodes from the front, only if size >= 2 m) moves to the top of the
+// thief's pool, device to device (cudaMemcpyPeerAsync: NVLink between two GPUs, a plain copy on one), order
+// preserved.  Both pools must be quiescent (no round in flight); the caller serialises access to both handles.
+int pool_steal_front(DevicePool& v, int vdev, cudaStream_t vs, DevicePool& t, int tdev, cudaStream_t ts, int m,
+                     long long min_cap, long long* n_stolen) {
+  *n_stolen = 0;
+  if (v.size < 2LL * m) return TSB_OK;
+  const long long want = v.size / 2;
+  TSB_CUDA(cudaSetDevice(tdev));
+  int rc = t.reserve(ts, want, min_cap);
+  if (rc != TSB_OK) return rc;
+  long long at = t.top();
+  if (t.rec == sizeof(tsb_pfsp_node)) at = (at + 1) & ~1LL;  // PFSP extents start on a 16-byte boundary
+  if (at + want > t.cap) {
+    rc = t.compact(ts, std::max<long long>(2 * t.cap, t.size + want + 1024));
+    if (rc != TSB_OK) return rc;
+    at = t.top();
+    if (t.rec == sizeof(tsb_pfsp_node)) at = (at + 1) & ~1LL;
+  }
+  TSB_CUDA(cudaSetDevice(vdev));
+  long long left = want, dst = at;
+  while (left > 0 && !v.ext.empty()) {
+    PoolExtent& x = v.ext.front();
+    const long long n = std::min(left, x.e - x.b);
+    TSB_CUDA(cudaMemcpyPeerAsync(t.arena[t.cur] + dst * t.rec, tdev, v.arena[v.cur] + x.b * v.rec, vdev,
+                                 static_cast<size_t>(n) * v.rec, vs));
+    x.b += n;
+    dst += n;
+    left -= n;
+    if (x.b == x.e) v.ext.erase(v.ext.begin());
+  }
+  TSB_CUDA(cudaStreamSynchronize(vs));
+  const long long got = want - left;
+  v.size -= got;
+  if (got) {
+    t.ext.push_back({at, at + got});
+    t.size += got;
+  }
+  *n_stolen = got;
+  return TSB_OK;
+}
+void enable_peer(int a, int b) {
+  if (a == b) return;
+  int can = 0;
+  if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
+    cudaSetDevice(a);
+    if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) (void)cudaGetLastError();  // (already enabled is fine)
+  }
+  (void)cudaGetLastError();
+}
+}  // namespace
+
 // ============================================================================ PFSP
 struct tsb_pfsp : Base {
   int jobs = 0, machines = 0, pairs = 0, mt = 0;  // mt = template machine count (5, 10 or 20)
@@ -1248,6 +1303,21 @@ int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rou
   return TSB_OK;
 }
 
+int tsb_nq_pool_steal(tsb_nq* victim, tsb_nq* thief, int m, int64_t* n_stolen) {
+  if (!victim || !thief || victim == thief || m < 1 || !n_stolen || victim->N != thief->N) return TSB_EINVAL;
+  nq_pool_setup(victim);
+  nq_pool_setup(thief);
+  enable_peer(thief->device, victim->device);
+  enable_peer(victim->device, thief->device);
+  long long n = 0;
+  victim->rounds.aux_valid = 0;
+  thief->rounds.aux_valid = 0;
+  int rc = pool_steal_front(victim->pool, victim->device, victim->stream, thief->pool, thief->device, thief->stream, m,
+                            nq_pool_min_cap(thief), &n);
+  *n_stolen = n;
+  return rc;
+}
+
 // diagnostics: cycles per round of the bare flag-exchange skeleton of the persistent kernel (nq_rounds.cuh)
 int tsb_debug_flag_exchange(int device, int rounds, int variant, int ctas, double* cycles_per_round) {
   if (!cycles_per_round || rounds < 1) return TSB_EINVAL;
@@ -1629,6 +1699,19 @@ int tsb_pfsp_pool_step(tsb_pfsp* h, int lb_kind, int m, int M, int64_t* best, in
   *n_children = nc;
   *n_solutions = ns;
   return TSB_OK;
+}
+
+int tsb_pfsp_pool_steal(tsb_pfsp* victim, tsb_pfsp* thief, int m, int64_t* n_stolen) {
+  if (!victim || !thief || victim == thief || m < 1 || !n_stolen || victim->jobs != thief->jobs) return TSB_EINVAL;
+  pfsp_pool_setup(victim);
+  pfsp_pool_setup(thief);
+  enable_peer(thief->device, victim->device);
+  enable_peer(victim->device, thief->device);
+  long long n = 0;
+  int rc = pool_steal_front(victim->pool, victim->device, victim->stream, thief->pool, thief->device, thief->stream, m,
+                            pfsp_pool_min_cap(thief), &n);
+  *n_stolen = n;
+  return rc;
 }
 
 int tsb_pfsp_pool_drain(tsb_pfsp* h, void* nodes, int64_t capacity, int64_t* n) {

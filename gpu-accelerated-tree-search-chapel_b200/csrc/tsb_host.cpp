@@ -15,6 +15,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -161,39 +164,174 @@ void nq_gpu_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool
   tsb_nq_destroy(h);
 }
 
-// the same loop with the task's pool resident on the device (tsb_nq_pool_*): popBackBulk, evaluate and
-// generate_children of a round are two kernels (count, build); the host reads three counters per round
-void nq_devpool_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResult& r) {
-  tsb_nq* h = nullptr;
-  const bool trace = std::getenv("TSB200_TRACE") != nullptr;
-  const double tt0 = now_s();
-  r.rc = tsb_nq_create(&h, device, N, g, M);
-  if (r.rc != TSB_OK) return;
-  const double tt1 = now_s();
-  r.rc = tsb_nq_pool_push(h, &pool.el[pool.front], static_cast<int64_t>(pool.size));
-  const double tt2 = now_s();
-  if (trace) std::fprintf(stderr, "[tsb200] device %d: create %.1f ms, first push (arena) %.1f ms\n", device,
-                          (tt1 - tt0) * 1e3, (tt2 - tt1) * 1e3);
-  pool.front = 0;
-  pool.size = 0;
-  if (r.rc == TSB_OK) {  // all rounds of step 2 (one persistent kernel for small M, two kernels per round otherwise)
+// ---- intra-node work stealing between the tasks' DEVICE pools (the reference steals between its per-GPU host
+// pools: nqueens_multigpu_chpl.chpl:255-312, pfsp_multigpu_chpl.chpl:438-495).  A task that runs out of work
+// (pool below m) asks the task with the fullest pool; the victim serves the request between two of its launches
+// (its pool is on its GPU and only it may touch it while kernels run): the oldest half of its pool moves to the
+// thief's GPU over NVLink (tsb_*_pool_steal = popFrontBulkFree, Pool_par.chpl:178-191).  Termination: all tasks
+// idle (util.chpl:16-30).  Counts are split-invariant for N-Queens and for PFSP with --ub 1, so stealing changes
+// the per-GPU shares, never the totals.
+struct StealBoard {
+  explicit StealBoard(int D_) : D(D_), size(D_, 0), request(D_, -1), reply(D_, 0), handle(D_, nullptr), failed(false) {}
+  const int D;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<long long> size;  // pool size every task last published
+  std::vector<int> request;     // request[v] = thief waiting for victim v, or -1
+  std::vector<int> reply;       // reply[thief]: 0 pending, 1 granted, -1 denied
+  std::vector<void*> handle;    // the tasks' library handles
+  bool failed;                  // a task could not create its handle: nobody steals
+  int idle = 0;
+  bool done = false;
+  uint64_t steals = 0;
+  // every task's handle exists before anybody steals
+  void publish_handle(int me, void* h, long long my_size) {
+    std::unique_lock<std::mutex> lk(mu);
+    handle[me] = h;
+    size[me] = my_size;
+    if (!h) failed = true;
+    cv.notify_all();
+    cv.wait(lk, [&] {
+      if (failed) return true;
+      for (void* x : handle)
+        if (!x) return false;
+      return true;
+    });
+  }
+};
+
+// what a device-pool task does between two launches: publish its pool size, serve a pending steal request
+template <class StealFn>
+int board_service(StealBoard* sb, int me, long long my_size, int m, StealFn&& steal) {
+  if (!sb) return TSB_OK;
+  int thief = -1;
+  {
+    std::lock_guard<std::mutex> lk(sb->mu);
+    sb->size[me] = my_size;
+    thief = sb->request[me];
+    sb->request[me] = -1;
+  }
+  if (thief < 0) return TSB_OK;
+  int64_t got = 0;
+  int rc = TSB_OK;
+  if (my_size >= 2LL * m && !sb->failed) rc = steal(sb->handle[me], sb->handle[thief], &got);
+  {
+    std::lock_guard<std::mutex> lk(sb->mu);
+    sb->reply[thief] = (rc == TSB_OK && got > 0) ? 1 : -1;
+    sb->size[me] = my_size - got;
+    if (got > 0) ++sb->steals;
+  }
+  sb->cv.notify_all();
+  return rc;
+}
+// out of work: true = stole something (keep going), false = everybody is idle (terminate)
+inline bool board_acquire(StealBoard* sb, int me, long long my_size, int m) {
+  if (!sb) return false;
+  std::unique_lock<std::mutex> lk(sb->mu);
+  sb->size[me] = my_size;
+  const auto deny_mine = [&] {  // I have nothing to give
+    if (sb->request[me] >= 0) {
+      sb->reply[sb->request[me]] = -1;
+      sb->request[me] = -1;
+      sb->cv.notify_all();
+    }
+  };
+  deny_mine();
+  ++sb->idle;
+  for (;;) {
+    if (sb->idle == sb->D) {
+      sb->done = true;
+      sb->cv.notify_all();
+      return false;
+    }
+    if (sb->done) return false;
+    int v = -1;
+    for (int i = 0; i < sb->D && !sb->failed; i++)  // the fullest pool nobody is already asking
+      if (i != me && sb->request[i] < 0 && sb->size[i] >= 2LL * m && (v < 0 || sb->size[i] > sb->size[v])) v = i;
+    if (v < 0) {
+      deny_mine();
+      sb->cv.wait_for(lk, std::chrono::microseconds(200));
+      continue;
+    }
+    sb->request[v] = me;
+    sb->reply[me] = 0;
+    --sb->idle;  // waiting for a victim is not being idle: the victim may hand over half of its pool
+    sb->cv.wait(lk, [&] { return sb->reply[me] != 0 || sb->done; });
+    if (sb->reply[me] > 0) return true;
+    if (sb->done) return false;
+    ++sb->idle;
+    sb->size[v] = std::min<long long>(sb->size[v], 2LL * m - 1);  // (it publishes again after its next launch)
+  }
+}
+
+// a task leaves on an error: nobody may wait for it any more
+inline void board_abort(StealBoard* sb, int me) {
+  if (!sb) return;
+  std::lock_guard<std::mutex> lk(sb->mu);
+  sb->failed = sb->done = true;
+  if (sb->request[me] >= 0) sb->reply[sb->request[me]] = -1;
+  sb->request[me] = -1;
+  sb->cv.notify_all();
+}
+
+// rounds per library call when other tasks may want to steal (a victim serves requests between calls)
+inline int64_t rounds_per_call(const StealBoard* sb, int M) { return !sb ? INT64_MAX : M <= 75776 ? 256 : 4; }
+
+// the offload loop with the task's pool resident on the device (tsb_nq_pool_*): all rounds of step 2 inside the
+// library (one persistent kernel for small M, two kernels per round otherwise); the host only reads counters
+void nq_devpool_rounds(tsb_nq* h, int m, int M, StealBoard* sb, int me, GpuTaskResult& r) {
+  const auto steal = [m](void* v, void* t, int64_t* got) {
+    return tsb_nq_pool_steal(static_cast<tsb_nq*>(v), static_cast<tsb_nq*>(t), m, got);
+  };
+  while (r.rc == TSB_OK) {
     uint64_t nr = 0, np = 0, nc = 0, ns = 0;
-    r.rc = tsb_nq_pool_run(h, m, M, INT64_MAX, &nr, &np, &nc, &ns);
+    r.rc = tsb_nq_pool_run(h, m, M, rounds_per_call(sb, M), &nr, &np, &nc, &ns);
+    if (r.rc != TSB_OK) break;
     r.tree += nc;
     r.sol += ns;
     r.offloads += nr;
     r.parents += np;
+    const long long size = tsb_nq_pool_size(h);
+    if (size >= m) {
+      r.rc = board_service(sb, me, size, m, steal);
+      continue;
+    }
+    if (!board_acquire(sb, me, size, m)) break;
   }
-  if (trace) std::fprintf(stderr, "[tsb200] device %d: %llu rounds in %.1f ms\n", device,
-                          static_cast<unsigned long long>(r.offloads), (now_s() - tt2) * 1e3);
-  if (r.rc == TSB_OK) {  // fewer than m nodes left: back to the host pool for step 3
+  if (r.rc != TSB_OK) board_abort(sb, me);
+}
+// pool -> device, all rounds, leftovers (fewer than m nodes) back to the host pool for step 3
+void nq_devpool_on(tsb_nq* h, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResult& r, StealBoard* sb = nullptr,
+                   int me = 0) {
+  const uint64_t l0 = tsb_nq_kernel_launches(h);
+  r.rc = tsb_nq_pool_push(h, &pool.el[pool.front], static_cast<int64_t>(pool.size));
+  pool.front = 0;
+  pool.size = 0;
+  if (sb) sb->publish_handle(me, r.rc == TSB_OK ? h : nullptr, tsb_nq_pool_size(h));
+  if (r.rc == TSB_OK) nq_devpool_rounds(h, m, M, sb, me, r);
+  if (r.rc == TSB_OK) {
     const int64_t left = tsb_nq_pool_size(h);
     std::vector<tsb_nq_node> rest(static_cast<size_t>(left) + 1);
     int64_t n = 0;
     r.rc = tsb_nq_pool_drain(h, rest.data(), left, &n);
     for (int64_t i = 0; i < n && r.rc == TSB_OK; i++) pool.pushBack(rest[i]);
   }
-  r.launches = tsb_nq_kernel_launches(h);
+  r.launches = tsb_nq_kernel_launches(h) - l0;
+}
+void nq_devpool_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResult& r,
+                     StealBoard* sb = nullptr, int me = 0) {
+  tsb_nq* h = nullptr;
+  const bool trace = std::getenv("TSB200_TRACE") != nullptr;
+  const double tt0 = now_s();
+  r.rc = tsb_nq_create(&h, device, N, g, M);
+  if (r.rc != TSB_OK) {
+    if (sb) sb->publish_handle(me, nullptr, 0);
+    return;
+  }
+  const double tt1 = now_s();
+  nq_devpool_on(h, m, M, pool, r, sb, me);
+  if (trace) std::fprintf(stderr, "[tsb200] device %d: create %.1f ms, %llu rounds in %.1f ms\n", device, (tt1 - tt0) * 1e3,
+                          static_cast<unsigned long long>(r.offloads), (now_s() - tt1) * 1e3);
   tsb_nq_destroy(h);
 }
 
@@ -372,24 +510,36 @@ void pfsp_gpu_task(int device, const tsb_pfsp_tables& t, int lb_kind, int m, int
 }
 
 // the same loop with the task's pool resident on the device (tsb_pfsp_pool_*)
-void pfsp_devpool_task(int device, const tsb_pfsp_tables& t, int lb_kind, int m, int M, Pool<tsb_pfsp_node>& pool,
-                       GpuTaskResult& r) {
-  tsb_pfsp* h = nullptr;
-  r.rc = tsb_pfsp_create_from_tables(&h, device, M, &t);
-  if (r.rc != TSB_OK) return;
+void pfsp_devpool_on(tsb_pfsp* h, int lb_kind, int m, int M, Pool<tsb_pfsp_node>& pool, GpuTaskResult& r,
+                     StealBoard* sb = nullptr, int me = 0) {
+  const uint64_t l0 = tsb_pfsp_kernel_launches(h);
   r.rc = tsb_pfsp_pool_push(h, &pool.el[pool.front], static_cast<int64_t>(pool.size));
   pool.front = 0;
   pool.size = 0;
+  if (sb) sb->publish_handle(me, r.rc == TSB_OK ? h : nullptr, tsb_pfsp_pool_size(h));
+  const auto steal = [m](void* v, void* t, int64_t* got) {
+    return tsb_pfsp_pool_steal(static_cast<tsb_pfsp*>(v), static_cast<tsb_pfsp*>(t), m, got);
+  };
+  int since_service = 0;
   while (r.rc == TSB_OK) {
     int64_t np = 0;
     uint64_t nc = 0, ns = 0;
     r.rc = tsb_pfsp_pool_step(h, lb_kind, m, M, &r.best, &np, &nc, &ns);
-    if (r.rc != TSB_OK || np == 0) break;
+    if (r.rc != TSB_OK) break;
+    if (np == 0) {
+      if (!board_acquire(sb, me, tsb_pfsp_pool_size(h), m)) break;
+      continue;
+    }
     r.tree += nc;
     r.sol += ns;
     ++r.offloads;
     r.parents += static_cast<uint64_t>(np);
+    if (sb && ++since_service >= 2) {  // publish the pool size / serve thieves every other round
+      since_service = 0;
+      r.rc = board_service(sb, me, tsb_pfsp_pool_size(h), m, steal);
+    }
   }
+  if (r.rc != TSB_OK) board_abort(sb, me);
   if (r.rc == TSB_OK) {
     const int64_t left = tsb_pfsp_pool_size(h);
     std::vector<tsb_pfsp_node> rest(static_cast<size_t>(left) + 1);
@@ -397,8 +547,22 @@ void pfsp_devpool_task(int device, const tsb_pfsp_tables& t, int lb_kind, int m,
     r.rc = tsb_pfsp_pool_drain(h, rest.data(), left, &n);
     for (int64_t i = 0; i < n && r.rc == TSB_OK; i++) pool.pushBack(rest[i]);
   }
-  r.launches = tsb_pfsp_kernel_launches(h);
+  r.launches = tsb_pfsp_kernel_launches(h) - l0;
+}
+void pfsp_devpool_task(int device, const tsb_pfsp_tables& t, int lb_kind, int m, int M, Pool<tsb_pfsp_node>& pool,
+                       GpuTaskResult& r, StealBoard* sb = nullptr, int me = 0) {
+  tsb_pfsp* h = nullptr;
+  r.rc = tsb_pfsp_create_from_tables(&h, device, M, &t);
+  if (r.rc != TSB_OK) {
+    if (sb) sb->publish_handle(me, nullptr, 0);
+    return;
+  }
+  pfsp_devpool_on(h, lb_kind, m, M, pool, r, sb, me);
   tsb_pfsp_destroy(h);
+}
+void pfsp_gpu_task_nosteal(int device, const tsb_pfsp_tables& t, int lb_kind, int m, int M, Pool<tsb_pfsp_node>& pool,
+                           GpuTaskResult& r, StealBoard*, int) {
+  pfsp_gpu_task(device, t, lb_kind, m, M, pool, r);
 }
 
 }  // namespace
@@ -538,11 +702,14 @@ int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out) {
 
 // part < 0: the whole search.  part >= 0: only task `part` of the D-way static split, on `device` (one rank of a
 // process-per-GPU launch): the step-1 tree is credited to part 0 and every part drains its own leftovers, so the
-// per-part counts add up to the whole search's.
-static int nq_search_device_impl(int N, int g, int m, int M, int D, int part, int device, tsb_search_stats* out) {
+// per-part counts add up to the whole search's.  `on` != nullptr: D = 1 on a handle the caller created (set-up
+// outside the search's timers, as the Chapel drivers' `on device var` declarations are).
+static int nq_search_device_impl(int N, int g, int m, int M, int D, int part, int device, tsb_nq* on,
+                                 tsb_search_stats* out) {
   if (!out || N < 1 || N > TSB_MAX_QUEENS || g < 1 || m < 1 || M < 1 || D < 1 || D > 8 || part >= D) return TSB_EINVAL;
   std::memset(out, 0, sizeof(*out));
-  if (int rc = tsb_init_devices(part < 0 ? D : device + 1); rc != TSB_OK) return rc;
+  if (!on)
+    if (int rc = tsb_init_devices(part < 0 ? D : device + 1); rc != TSB_OK) return rc;
   Pool<tsb_nq_node> pool;
   tsb_nq_node root{};
   for (int i = 0; i < N; i++) root.board[i] = static_cast<uint8_t>(i);
@@ -556,10 +723,13 @@ static int nq_search_device_impl(int N, int g, int m, int M, int D, int part, in
   }
   double t1 = now_s();
   out->t_step1 = t1 - t0;
-  // step 2: every task's pool moves to its device and stays there (same static split as tsb_nq_search)
+  // step 2: every task's pool moves to its device and stays there (same static split as tsb_nq_search); tasks
+  // that run dry steal from the fullest device pool over NVLink
   std::vector<GpuTaskResult> res(D);
   const int ndev = std::max(1, tsb_device_count());
-  if (part >= 0) {
+  if (on) {
+    nq_devpool_on(on, m, M, pool, res[0]);
+  } else if (part >= 0) {
     if (part != 0) tree = sol = 0;  // step 1 is credited to part 0
     std::vector<Pool<tsb_nq_node>> multi;
     if (D == 1) {
@@ -575,12 +745,15 @@ static int nq_search_device_impl(int N, int g, int m, int M, int D, int part, in
   } else {
     std::vector<Pool<tsb_nq_node>> multi;
     static_split(pool, D, multi);
+    StealBoard board(D);
+    StealBoard* sb = std::getenv("TSB200_NO_STEAL") ? nullptr : &board;
     std::vector<std::thread> th;
     for (int gid = 0; gid < D; gid++)
-      th.emplace_back([&, gid] { nq_devpool_task(gid % ndev, N, g, m, M, multi[gid], res[gid]); });
+      th.emplace_back([&, gid] { nq_devpool_task(gid % ndev, N, g, m, M, multi[gid], res[gid], sb, gid); });
     for (auto& x : th) x.join();
     for (int gid = 0; gid < D; gid++)
       while (multi[gid].popBack(parent)) pool.pushBack(parent);
+    out->steals = board.steals;
   }
   for (int gid = 0; gid < D; gid++) {
     if (res[gid].rc != TSB_OK) return res[gid].rc;
@@ -601,7 +774,7 @@ static int nq_search_device_impl(int N, int g, int m, int M, int D, int part, in
 }
 
 static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, bool devpool, int part, int device,
-                            tsb_search_stats* out) {
+                            tsb_pfsp* on, tsb_search_stats* out) {
   if (!out || lb_kind < 0 || lb_kind > 2 || (ub != 0 && ub != 1) || m < 1 || M < 1 || D < 1 || D > 8 || part >= D)
     return TSB_EINVAL;
   std::memset(out, 0, sizeof(*out));
@@ -609,7 +782,8 @@ static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, 
   tsb_pfsp_tables& t = tv[0];
   int rc = tsb_pfsp_tables_build(&t, inst);
   if (rc != TSB_OK) return rc;
-  if (rc = tsb_init_devices(part < 0 ? D : device + 1); rc != TSB_OK) return rc;  // contexts exist before the timers start
+  if (!on)
+    if (rc = tsb_init_devices(part < 0 ? D : device + 1); rc != TSB_OK) return rc;  // contexts exist before the timers start
   HostBounds hb(t);
   int64_t best = ub == 1 ? tsb_taillard_best_ub(inst) : INT64_MAX;  // pfsp_gpu_chpl.chpl:37
   Pool<tsb_pfsp_node> pool;
@@ -629,8 +803,10 @@ static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, 
   std::vector<GpuTaskResult> res(D);
   const int ndev = std::max(1, tsb_device_count());
   for (auto& r : res) r.best = best;  // per-task best_l = best (pfsp_multigpu_chpl.chpl:384)
-  auto task = devpool ? pfsp_devpool_task : pfsp_gpu_task;
-  if (part >= 0) {  // one task of the split (see nq_search_device_impl)
+  auto task = devpool ? pfsp_devpool_task : pfsp_gpu_task_nosteal;
+  if (on) {
+    pfsp_devpool_on(on, lb_kind, m, M, pool, res[0]);
+  } else if (part >= 0) {  // one task of the split (see nq_search_device_impl)
     if (part != 0) tree = sol = 0;
     std::vector<Pool<tsb_pfsp_node>> multi;
     if (D == 1) {
@@ -639,19 +815,23 @@ static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, 
     } else {
       static_split(pool, D, multi);
     }
-    task(device, t, lb_kind, m, M, multi[part], res[part]);
+    task(device, t, lb_kind, m, M, multi[part], res[part], nullptr, 0);
     while (multi[part].popBack(parent)) pool.pushBack(parent);
   } else if (D == 1) {
-    task(0, t, lb_kind, m, M, pool, res[0]);
+    task(0, t, lb_kind, m, M, pool, res[0], nullptr, 0);
   } else {
     std::vector<Pool<tsb_pfsp_node>> multi;
     static_split(pool, D, multi);
+    StealBoard board(D);
+    // (stealing keeps the counts only when `best` is constant: --ub 1)
+    StealBoard* sb = (devpool && ub == 1 && !std::getenv("TSB200_NO_STEAL")) ? &board : nullptr;
     std::vector<std::thread> th;
     for (int gid = 0; gid < D; gid++)
-      th.emplace_back([&, gid] { task(gid % ndev, t, lb_kind, m, M, multi[gid], res[gid]); });
+      th.emplace_back([&, gid] { task(gid % ndev, t, lb_kind, m, M, multi[gid], res[gid], sb, gid); });
     for (auto& x : th) x.join();
     for (int gid = 0; gid < D; gid++)
       while (multi[gid].popBack(parent)) pool.pushBack(parent);
+    out->steals = board.steals;
   }
   for (int gid = 0; gid < D; gid++) {
     if (res[gid].rc != TSB_OK) return res[gid].rc;
@@ -674,22 +854,30 @@ static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, 
 }
 
 int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* out) {
-  return nq_search_device_impl(N, g, m, M, D, -1, 0, out);
+  return nq_search_device_impl(N, g, m, M, D, -1, 0, nullptr, out);
 }
 int tsb_nq_search_device_part(int N, int g, int m, int M, int D, int part, int device, tsb_search_stats* out) {
   if (part < 0) return TSB_EINVAL;
-  return nq_search_device_impl(N, g, m, M, D, part, device, out);
+  return nq_search_device_impl(N, g, m, M, D, part, device, nullptr, out);
+}
+int tsb_nq_search_on(tsb_nq* h, int N, int m, int M, tsb_search_stats* out) {
+  if (!h) return TSB_EINVAL;
+  return nq_search_device_impl(N, 1, m, M, 1, -1, 0, h, out);
 }
 int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out) {
-  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, false, -1, 0, out);
+  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, false, -1, 0, nullptr, out);
 }
 int tsb_pfsp_search_device(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out) {
-  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, true, -1, 0, out);
+  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, true, -1, 0, nullptr, out);
 }
 int tsb_pfsp_search_device_part(int inst, int lb_kind, int ub, int m, int M, int D, int part, int device,
                                 tsb_search_stats* out) {
   if (part < 0) return TSB_EINVAL;
-  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, true, part, device, out);
+  return pfsp_search_impl(inst, lb_kind, ub, m, M, D, true, part, device, nullptr, out);
+}
+int tsb_pfsp_search_on(tsb_pfsp* h, int inst, int lb_kind, int ub, int m, int M, tsb_search_stats* out) {
+  if (!h) return TSB_EINVAL;
+  return pfsp_search_impl(inst, lb_kind, ub, m, M, 1, true, -1, 0, h, out);
 }
 
 }  // extern "C"

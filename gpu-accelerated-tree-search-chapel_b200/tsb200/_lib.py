@@ -44,7 +44,7 @@ class SearchStats(C.Structure):
         ("explored_tree", C.c_uint64), ("explored_sol", C.c_uint64), ("best", C.c_int64),
         ("t_step1", C.c_double), ("t_step2", C.c_double), ("t_step3", C.c_double),
         ("offloads", C.c_uint64), ("offloaded_parents", C.c_uint64), ("kernel_launches", C.c_uint64),
-        ("per_gpu_tree", C.c_uint64 * 8),
+        ("per_gpu_tree", C.c_uint64 * 8), ("steals", C.c_uint64),
     ]
 
 
@@ -67,6 +67,8 @@ SYMBOLS = {
     "tsb_nq_pool_size": (_i64, [_vp]),
     "tsb_nq_pool_step": (_i, [_vp, _i, _i, C.POINTER(_i64), C.POINTER(_u64), C.POINTER(_u64)]),
     "tsb_nq_pool_drain": (_i, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    "tsb_nq_pool_steal": (_i, [_vp, _vp, _i, C.POINTER(_i64)]),
+    "tsb_pfsp_pool_steal": (_i, [_vp, _vp, _i, C.POINTER(_i64)]),
     "tsb_nq_pool_run": (_i, [_vp, _i, _i, _i64, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "tsb_nq_register_host": (_i, [_vp, _vp, C.c_size_t]),
     "tsb_nq_unregister_host": (_i, [_vp, _vp]),
@@ -97,6 +99,8 @@ SYMBOLS = {
     "tsb_nq_search_device": (_i, [_i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
     "tsb_pfsp_search": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
     "tsb_pfsp_search_device": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
+    "tsb_nq_search_on": (_i, [_vp, _i, _i, _i, C.POINTER(SearchStats)]),
+    "tsb_pfsp_search_on": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
     "tsb_nq_search_device_part": (_i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
     "tsb_pfsp_search_device_part": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
 }

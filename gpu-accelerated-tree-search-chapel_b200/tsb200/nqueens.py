@@ -96,6 +96,17 @@ class NQueensEvaluator:
         check(lib().tsb_nq_pool_step(self._h, m, M, C.byref(np_), C.byref(nc), C.byref(ns)), "tsb_nq_pool_step")
         return int(np_.value), int(nc.value), int(ns.value)
 
+    def search(self, m: int = 25, M: int | None = None) -> SearchStats:
+        """the whole 3-step search (nqueens_gpu_chpl.chpl:152-248) with the pool of step 2 on this handle's device"""
+        st = SearchStats()
+        check(lib().tsb_nq_search_on(self._h, self.N, m, self.M if M is None else M, C.byref(st)), "tsb_nq_search_on")
+        return st
+
+    def pool_steal_from(self, victim: "NQueensEvaluator", m: int) -> int:
+        got = C.c_int64(0)
+        check(lib().tsb_nq_pool_steal(victim._h, self._h, m, C.byref(got)), "tsb_nq_pool_steal")
+        return int(got.value)
+
     def pool_run(self, m: int, M: int, max_rounds: int = 2**62):
         """(rounds, parents popped, children appended, solutions) of up to max_rounds device-side offload rounds
         (until the pool holds fewer than m nodes); one persistent kernel for M <= 512 x #SMs"""

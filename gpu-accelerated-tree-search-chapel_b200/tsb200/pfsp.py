@@ -114,6 +114,19 @@ class PfspEvaluator:
               "tsb_pfsp_pool_step")
         return int(np_.value), int(nc.value), int(ns.value), int(b.value)
 
+    def search(self, inst: int, lb, ub: int = 1, m: int = 25, M: int | None = None) -> SearchStats:
+        """the whole 3-step search (pfsp_gpu_chpl.chpl:306-431) with the pool of step 2 on this handle's device"""
+        kind = LB_NAMES[lb] if isinstance(lb, str) else int(lb)
+        st = SearchStats()
+        check(lib().tsb_pfsp_search_on(self._h, inst, kind, ub, m, self.M if M is None else M, C.byref(st)),
+              "tsb_pfsp_search_on")
+        return st
+
+    def pool_steal_from(self, victim: "PfspEvaluator", m: int) -> int:
+        got = C.c_int64(0)
+        check(lib().tsb_pfsp_pool_steal(victim._h, self._h, m, C.byref(got)), "tsb_pfsp_pool_steal")
+        return int(got.value)
+
     def pool_drain(self) -> np.ndarray:
         n = self.pool_size
         out = np.empty(max(n, 1), dtype=PFSP_NODE_DTYPE)

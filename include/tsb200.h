@@ -131,6 +131,11 @@ int tsb_nq_pool_drain(tsb_nq* h, void* nodes, int64_t capacity_nodes, int64_t* n
  * 512 x #SMs (the reference's default --M 50000) the whole loop of nqueens_gpu_chpl.chpl:197-215 runs inside ONE
  * persistent cooperative kernel (two flag exchanges through L2 per round instead of two launches and a host
  * round trip); larger M falls back to one tsb_nq_pool_step per round.  Totals over the rounds come back. */
+/* work stealing between two device pools (the reference steals between its per-GPU host pools,
+ * nqueens_multigpu_chpl.chpl:255-312): if the victim holds >= 2 m nodes, the oldest size / 2 of them
+ * (popFrontBulkFree, lib/commons/Pool_par.chpl:178-191) move to the top of the thief's pool, device to device
+ * (NVLink between two GPUs).  No round may be in flight on either handle; the caller serialises the two. */
+int tsb_nq_pool_steal(tsb_nq* victim, tsb_nq* thief, int m, int64_t* n_stolen);
 int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rounds, uint64_t* n_parents,
                     uint64_t* n_children, uint64_t* n_solutions);
 
@@ -190,6 +195,7 @@ int64_t tsb_pfsp_pool_size(const tsb_pfsp* h);
 int tsb_pfsp_pool_step(tsb_pfsp* h, int lb_kind, int m, int M, int64_t* best, int64_t* n_parents,
                        uint64_t* n_children, uint64_t* n_solutions);
 int tsb_pfsp_pool_drain(tsb_pfsp* h, void* nodes, int64_t capacity_nodes, int64_t* n);
+int tsb_pfsp_pool_steal(tsb_pfsp* victim, tsb_pfsp* thief, int m, int64_t* n_stolen);
 int tsb_pfsp_register_host(tsb_pfsp* h, void* ptr, size_t bytes);
 int tsb_pfsp_unregister_host(tsb_pfsp* h, void* ptr);
 int tsb_pfsp_set_xfer(tsb_pfsp* h, int mode);
@@ -226,14 +232,20 @@ typedef struct {
   double t_step1, t_step2, t_step3; /* seconds */
   uint64_t offloads, offloaded_parents, kernel_launches;
   uint64_t per_gpu_tree[8];
+  uint64_t steals;                /* successful steals between device pools (D > 1, one process) */
 } tsb_search_stats;
 
 /* nqueens_gpu_chpl.chpl:152-248 / nqueens_multigpu_chpl.chpl:158-352 */
 int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out);
 /* the same 3-step search with the pool(s) of step 2 resident on the device(s) (tsb_nq_pool_*): identical
  * chunk sequence, identical counts; the host only reads three counters per round.  D > 1 = the same static
- * strided split, one device pool per GPU. */
+ * strided split, one device pool per GPU; a task whose pool runs dry steals the oldest half of the fullest device
+ * pool over NVLink (the reference's intra-node work stealing, nqueens_multigpu_chpl.chpl:255-312, moved to the
+ * device pools; env TSB200_NO_STEAL=1 = the static split alone). */
 int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* out);
+/* the D = 1 search on a handle the caller created (N and M_max >= M must match): set-up stays outside the
+ * search's timers, as the `on device var` declarations of the Chapel drivers do */
+int tsb_nq_search_on(tsb_nq* h, int N, int m, int M, tsb_search_stats* out);
 /* one task of that D-way split, on `device` — for process-per-GPU launches (one rank = one part): step 1 is
  * credited to part 0 and each part drains its own leftovers, so the parts' counts add up to the whole search */
 int tsb_nq_search_device_part(int N, int g, int m, int M, int D, int part, int device, tsb_search_stats* out);
@@ -243,6 +255,7 @@ int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_sear
 int tsb_pfsp_search_device(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out);
 int tsb_pfsp_search_device_part(int inst, int lb_kind, int ub, int m, int M, int D, int part, int device,
                                 tsb_search_stats* out);
+int tsb_pfsp_search_on(tsb_pfsp* h, int inst, int lb_kind, int ub, int m, int M, tsb_search_stats* out);
 
 #ifdef __cplusplus
 }

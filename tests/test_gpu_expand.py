@@ -86,7 +86,8 @@ def test_device_pool_compaction_and_growth(golden_dir, monkeypatch):
 
 @pytest.mark.parametrize("N,m,M,D", [(10, 25, 50000, 1), (12, 25, 50000, 1), (12, 5, 300, 1), (13, 25, 4096, 1),
                                      (14, 25, 50000, 1), (15, 25, 1 << 20, 1), (13, 25, 2000, 3), (14, 25, 50000, 4)])
-def test_device_resident_search_counts(golden_dir, N, m, M, D):
+def test_device_resident_search_counts(golden_dir, N, m, M, D, monkeypatch):
+    monkeypatch.setenv("TSB200_NO_STEAL", "1")  # the static split alone: the reference driver's chunk sequence
     counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
     st = tsb200.nqueens_search_device(N, 1, m, M, D)
     assert (st.explored_tree, st.explored_sol) == (counts["tree"], counts["sol"])
@@ -96,6 +97,40 @@ def test_device_resident_search_counts(golden_dir, N, m, M, D):
         assert 0 < st.kernel_launches < max(16, st.offloads // 4 + 16)
     else:
         assert st.kernel_launches == 2 * st.offloads  # count, build
+
+
+@pytest.mark.parametrize("N,m,M,D", [(13, 25, 2000, 3), (14, 25, 50000, 4), (15, 25, 50000, 8), (15, 25, 1 << 18, 4),
+                                     (12, 5, 300, 2)])
+def test_device_resident_search_with_work_stealing(golden_dir, N, m, M, D):
+    """D tasks (wrapping onto the GPUs present), device pools, stealing between them: the totals are those of the
+    reference whatever the steals did to the per-GPU shares"""
+    counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
+    st = tsb200.nqueens_search_device(N, 1, m, M, D)
+    assert (st.explored_tree, st.explored_sol) == (counts["tree"], counts["sol"])
+    assert sum(st.per_gpu_tree[:D]) <= st.explored_tree
+
+
+def test_pool_steal_moves_the_oldest_half_in_order():
+    N, m = 12, 25
+    rng = np.random.default_rng(12)
+    nodes = rand_nq(rng, N, 1001, depth_lo=1, depth_hi=5)
+    with tsb200.NQueensEvaluator(N, M=5000) as victim, tsb200.NQueensEvaluator(N, M=5000) as thief:
+        victim.pool_push(nodes)
+        own = rand_nq(rng, N, 7, depth_lo=1, depth_hi=5)
+        thief.pool_push(own)
+        assert thief.pool_steal_from(victim, m) == 500  # size / 2 from the front (Pool_par.chpl:178-191)
+        assert (victim.pool_size, thief.pool_size) == (501, 507)
+        assert thief.pool_steal_from(victim, 300) == 0 and victim.pool_size == 501  # below 2 m: nothing moves
+        assert thief.pool_drain().tobytes() == np.concatenate([own, nodes[:500]]).tobytes()
+        assert victim.pool_drain().tobytes() == np.ascontiguousarray(nodes[500:]).tobytes()
+        # and the pools keep working after a steal: the stolen half explored by the thief, the rest by the victim
+        victim.pool_push(nodes[:200])
+        assert thief.pool_steal_from(victim, m) == 100
+        a, b = victim.pool_run(1, 5000), thief.pool_run(1, 5000)
+    with tsb200.NQueensEvaluator(N, M=5000) as one:
+        one.pool_push(nodes[:200])
+        c = one.pool_run(1, 5000)
+    assert a[2] + b[2] == c[2] and a[3] + b[3] == c[3]
 
 
 @pytest.mark.parametrize("N,m,M,rounds", [(11, 25, 700, 40), (12, 5, 300, 200), (13, 25, 5000, 37), (14, 25, 50000, 11),

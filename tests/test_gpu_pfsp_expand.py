@@ -106,9 +106,10 @@ def test_device_pool_is_byte_identical_to_the_reference_pool(lb):
                                               (14, "lb2", 1, 25, 50000, 1), (14, "lb1", 1, 25, 3000, 3),
                                               (14, "lb1", 1, 5, 1 << 20, 1), (14, "lb2", 1, 25, 700, 2),
                                               (14, "lb1_d", 0, 25, 50000, 1)])
-def test_device_resident_search_counts(golden_dir, inst, lb, ub, m, M, D):
+def test_device_resident_search_counts(golden_dir, inst, lb, ub, m, M, D, monkeypatch):
     """whole searches: identical explored tree / solutions / optimum and the same chunk sequence as the reference
     driver (ub = 0: the incumbent is found on the way, several slow rounds; single task, so still deterministic)"""
+    monkeypatch.setenv("TSB200_NO_STEAL", "1")  # the static split alone: the reference driver's chunk sequence
     st = tsb200.pfsp_search_device(inst, lb, ub, m, M, D)
     ref = po.pfsp_search_offload(inst, tsb200.LB_NAMES[lb], ub, m, M, D)
     assert (st.explored_tree, st.explored_sol, st.best) == (ref.tree, ref.sol, ref.best)
@@ -117,6 +118,29 @@ def test_device_resident_search_counts(golden_dir, inst, lb, ub, m, M, D):
         counts = json.load(open(os.path.join(golden_dir, "counts.json")))["pfsp"]
         key = f"ta{inst:03d}_lb{tsb200.LB_NAMES[lb]}_ub1"
         assert (st.explored_tree, st.explored_sol, st.best) == (counts[key]["tree"], counts[key]["sol"], counts[key]["best"])
+
+
+@pytest.mark.parametrize("inst,lb,m,M,D", [(14, "lb1", 25, 3000, 3), (14, "lb1_d", 25, 50000, 4), (14, "lb2", 25, 700, 2),
+                                           (14, "lb1", 25, 500, 8)])
+def test_device_resident_search_with_work_stealing(golden_dir, inst, lb, m, M, D):
+    """D tasks with device pools that steal from each other (--ub 1: the counts do not depend on who explores what)"""
+    st = tsb200.pfsp_search_device(inst, lb, 1, m, M, D)
+    counts = json.load(open(os.path.join(golden_dir, "counts.json")))["pfsp"]
+    key = f"ta{inst:03d}_lb{tsb200.LB_NAMES[lb]}_ub1"
+    assert (st.explored_tree, st.explored_sol, st.best) == (counts[key]["tree"], counts[key]["sol"], counts[key]["best"])
+
+
+def test_search_on_a_precreated_handle(golden_dir):
+    counts = json.load(open(os.path.join(golden_dir, "counts.json")))["pfsp"]["ta014_lb1_ub1"]
+    with tsb200.PfspEvaluator(14, M=50000) as ev:
+        for _ in range(3):  # the handle (tables, arena, side arrays) is reused
+            st = ev.search(14, "lb1", 1, 25, 50000)
+            assert (st.explored_tree, st.explored_sol, st.best) == (counts["tree"], counts["sol"], counts["best"])
+    nq = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"]["13"]
+    with tsb200.NQueensEvaluator(13, M=50000) as ev:
+        for _ in range(3):
+            st = ev.search(25, 50000)
+            assert (st.explored_tree, st.explored_sol) == (nq["tree"], nq["sol"])
 
 
 def test_pool_compaction_and_growth(monkeypatch):
