@@ -1,34 +1,38 @@
 #!/usr/bin/env python
-"""bench.py — batch node-evaluation throughput (Mnodes/s) on B200, BASELINE.json's metric.
+"""bench.py — Mnodes/s of the GPU-offloaded tree search on B200, BASELINE.json's metric.
 
-A *step* is one pass of the hot path over one batch of synthetic parent nodes:
-  * headline workload (BASELINE.json configs[1]): N-Queens N=17, g=1 — a batch of --M parents whose depths
-    follow the explored-tree depth histogram of the N=17 search (what the reference's step-2 loop offloads),
-    boards = random conflict-free prefixes + random remaining order;
-  * secondary workload reported in the same line under "pfsp": PFSP ta014, lb1, ub=1 — parents with the
-    ta014/lb1 offload depth histogram, random permutations.
-`value`  = parents evaluated per second, inputs and outputs resident in HBM (device entry point, one kernel
-           launch per step, CUDA events on the launching stream, max over ranks);
-`e2e`    = the same metric through the reference-facing C-ABI call tsb_nq_evaluate / tsb_pfsp_evaluate with
-           HOST buffers: the copy of the chunk to the device and of the labels/bounds back happen inside the
-           timed region, every step;
-`roofline` = algorithmic bytes per launch (21 B + N B per parent; 88 B + 80 B for PFSP) / measured kernel time,
-           against MEASURED_PEAKS.json's HBM copy bandwidth;
-`at_M50000` = the same three numbers at the reference's default chunk size --M 50000 (launch-latency bound:
-           1.9 MB per launch), which is what one offload of the unmodified Chapel driver would see.
-`search`   = whole searches (explored tree / wall time, the quantity the reference prints) with the pool of
-           step 2 resident in HBM (tsb_*_search_device: count + build kernels per round, nothing but three
-           counters crosses PCIe): N-Queens N=17 at --M and at the reference's --M 50000, PFSP ta014/lb1 and
-           ta020/lb2 at --M 50000 (BASELINE configs 2-4).  Counts are checked against the reference's.  With
-           N > 1 ranks every rank runs one task of the reference's static N-way split of the warm-up pool
-           (tsb_*_search_device_part) on its own GPU; tree = sum over ranks, time = max over ranks ("strong").
-Between timed iterations the inputs/outputs rotate over buffer sets whose total footprint exceeds the 126 MB L2.
+HEADLINE (value / e2e / roofline, BASELINE configs[1]): the N-Queens N=17 search with the reference's defaults
+g=1 m=25 --M 50000.  A *step* is one whole search; Mnodes/s = explored tree / time, the quantity the reference
+prints (nqueens_gpu_chpl.chpl:39-46).  Every step the explored tree and the solution count are checked against
+the reference's (8 017 021 931 / 95 815 104).
+  value : step 2 (the offload loop, nqueens_gpu_chpl.chpl:197-215) with the warm-up pool already resident in HBM
+          on a pre-created handle — tsb_nq_pool_run, CUDA events on the handle's stream around it;
+          children produced / event time
+  e2e   : the whole search through the reference-facing C-ABI call with host inputs and outputs
+          (tsb_nq_search_on: step 1 on the CPU, the warm-up pool copied host->device, all rounds, the leftover
+          nodes and the counters copied device->host, step 3 on the CPU), wall clock; explored tree / time
+  roofline : nq_rounds_kernel, the one kernel of that timed region: 21 B read per parent + 21 B written per child
+          (= 42 B per explored node) / event time.  At --M 50000 a round moves ~2 MB and is bound by the two flag
+          exchanges that order it after the previous round, not by HBM; the bandwidth-bound kernels are listed
+          under "kernels" with their own fractions
+  N > 1 (torchrun) : the same search split over N GPUs (static split of the warm-up pool + stealing between the
+          device pools over NVLink), driven by rank 0 in one process with one host thread per GPU, as the
+          reference's multi-GPU driver is one process with one task per GPU; the other ranks hold their GPU and
+          the NCCL barrier.  scaling = strong (the tree is fixed).
+SECONDARY (same line):
+  batch   : the batch evaluators of round 1 — device-resident value, host-buffer e2e (registered arrays, zero-copy
+            over PCIe) and HBM roofline of tsb_nq_evaluate (N=17, --big-M and 50000 parents), tsb_pfsp_evaluate
+            lb1 (ta014) and lb2 (ta020); with N > 1 ranks every rank evaluates its own batch (weak scaling)
+  search  : other whole searches on pre-created handles: N=17 at --big-M (two bandwidth-bound kernels per round),
+            PFSP ta014/lb1 and ta020/lb2 at --M 50000 (BASELINE configs 2-3), ta020/lb1_d with the Chapel min_heads
+            (836 490 312 nodes); at N = 8: N=19 --D 8 (BASELINE configs[4])
+  kernels : per kernel: us per launch, achieved GB/s, fraction of the measured HBM peak, DRAM traffic of the ncu
+            capture under profiles/ (parsed at run time)
+  cpu_baseline : the reference's own sequential search code (oracle/_ref: nqueens_c.c's pool / isSafe / decompose)
+            on all host cores (subtrees handed out dynamically) and on one core
 
-`--impl reference` times the reference's own CPU implementation of the same path (its isSafe / lb1_bound
-loops, compiled unmodified into oracle/_ref; the oracle port if that is absent) on all host threads.
-
-N > 1 (torchrun): every rank evaluates its own batch on its own GPU (the path shards by parents, no
-collective in the data path); value = total parents / max-over-ranks time; scaling = weak.
+`--impl reference`: the reference's CPU search on all host threads as its own arm; each step is a bounded sample of
+the workload (the whole N=16 / 15 / 14 search, by core count: the same code per node, 1/7 .. 1/300 of the tree).
 """
 import argparse
 import json
@@ -228,6 +232,33 @@ def dist_max_sum(world, t_seconds, units, device):
     return float(t.item()), float(u.item())
 
 
+
+N_HEAD, M_HEAD, m_HEAD = 17, 50000, 25
+GOLDEN_NQ = {12: (856188, 14200), 13: (4674889, 73712), 14: (27358552, 365596), 15: (171129071, 2279184),
+             16: (1141190302, 14772512), 17: (8017021931, 95815104), 18: (59365844490, 666090624),
+             19: (461939618823, 4968057848)}  # tests/golden/counts.json (reference binaries) + known solution counts
+GOLDEN_PFSP = {(14, "lb1"): (2573652, 2648, 1377), (20, "lb2"): (4870386, 0, 1591),
+               (20, "lb1_d"): (836490312, 3764, 1591)}  # (20, lb1_d): Chapel min_heads semantics
+NODE_BYTES = 42  # 21 B read per parent + 21 B written per child: algorithmic HBM bytes per explored node
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def make_config(gpus, M=M_HEAD):
+    return {"workload": f"N-Queens N={N_HEAD} g=1 m={m_HEAD} --M {M}: whole search, Mnodes/s = explored tree / time "
+                        "(BASELINE configs[1]; the reference's default chunk size)",
+            "N": N_HEAD, "g": 1, "m": m_HEAD, "M": M,
+            "parallelism": f"{gpus} GPU(s): static split of the warm-up pool, one device pool per GPU, stealing "
+                           "between device pools",
+            "l2": "every step streams its whole pool through HBM (8.0 G nodes x 42 B >> the 126 MB L2); no buffer "
+                  "is reused between steps"}
+
+
 # ----------------------------------------------------------------------------------------- our arm
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -236,8 +267,119 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel_substr, files):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first kernel whose name contains `kernel_substr` in the
+    ncu summaries under profiles/ (newest round first); None if there is no capture"""
+    import re
+    unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for f in files:
+        path = os.path.join(ROOT, "profiles", f)
+        if not os.path.exists(path):
+            continue
+        cur, got = None, {}
+        for line in open(path):
+            if line.startswith("kernel:"):
+                if got:
+                    break
+                cur, got = (line if kernel_substr in line else None), {}
+            elif cur:
+                mm = re.match(r"\s+dram__bytes_(read|write)\.sum\s+([\d.]+)\s+(\w+)", line)
+                if mm:
+                    got[mm.group(1)] = float(mm.group(2)) * unit.get(mm.group(3), 1)
+        if "read" in got:  # (the summaries leave out counters that are 0)
+            return {"bytes": got["read"] + got.get("write", 0.0), "source": f"profiles/{f}"}
+    return None
+
+
+def run_headline_1gpu(steps, warmup, device_index, M=M_HEAD, N=N_HEAD):
+    """value (step 2 on a resident pool, CUDA events) and e2e (whole search through the C ABI) on one GPU"""
+    import torch
+
+    import tsb200
+    dev = torch.device(f"cuda:{device_index}")
+    torch.cuda.set_device(dev)
+    t_c0 = time.perf_counter()
+    ev = tsb200.NQueensEvaluator(N, 1, M, device=device_index)
+    t_create = time.perf_counter() - t_c0
+    warm, wtree, wsol = tsb200.nqueens_warmup(N, m_HEAD)
+    stream = torch.cuda.ExternalStream(ev.stream, device=dev)
+    want = GOLDEN_NQ[N]
+    for _ in range(warmup):
+        st = ev.search(m_HEAD, M)
+        assert (st.explored_tree, st.explored_sol) == want, "search counts differ from the reference's"
+    # ---- value: the offload loop on a pool that is already in HBM
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_dev, nodes, rounds = 0.0, 0, 0
+    l0 = ev.kernel_launches
+    torch.cuda.synchronize()
+    with ClockSampler(device_index) as clk:
+        for _ in range(steps):
+            ev.pool_push(warm)
+            launches_before = ev.kernel_launches
+            e0.record(stream)
+            nr, npar, nc, ns = ev.pool_run(m_HEAD, M)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t_dev += e0.elapsed_time(e1) / 1e3
+            nodes += nc
+            rounds += nr
+            launches_per_step = ev.kernel_launches - launches_before
+            ev.pool_drain()
+        launches = ev.kernel_launches - l0
+        # ---- e2e: the whole search, host in / host out
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tree = 0
+        for _ in range(steps):
+            st = ev.search(m_HEAD, M)
+            tree += st.explored_tree
+            assert (st.explored_tree, st.explored_sol) == want, "search counts differ from the reference's"
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+    ev.close()
+    return {"t_dev": t_dev, "nodes": nodes, "rounds": rounds, "t_e2e": t_e2e, "tree": tree, "launches": launches,
+            "launches_per_step": launches_per_step, "clocks": clk.summary(), "create_ms": t_create * 1e3,
+            "h2d": warm.nbytes, "d2h": 64 + m_HEAD * 21, "offloads": int(st.offloads), "steps": steps}
+
+
+def run_headline_multi(steps, warmup, world, rank, M=M_HEAD, N=N_HEAD):
+    """N > 1: rank 0 drives all `world` GPUs in one process (one host thread, handle and device pool per GPU, the
+    reference's multi-GPU structure); the other ranks keep their GPU busy with nothing and meet rank 0 at barriers"""
+    import torch
+
+    import tsb200
+    dev = torch.device(f"cuda:{rank}")
+    out = None
+    dist_barrier(world)
+    if rank == 0:
+        want = GOLDEN_NQ[N]
+        for _ in range(warmup):
+            st = tsb200.nqueens_search_device(N, 1, m_HEAD, M, world)
+            assert (st.explored_tree, st.explored_sol) == want
+        t2, tree, launches, steals = 0.0, 0, 0, 0
+        shares = None
+        with ClockSampler(0) as clk:
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                st = tsb200.nqueens_search_device(N, 1, m_HEAD, M, world)
+                assert (st.explored_tree, st.explored_sol) == want, "search counts differ from the reference's"
+                t2 += st.t_step2
+                tree += st.explored_tree
+                launches += st.kernel_launches
+                steals += st.steals
+                shares = [st.per_gpu_tree[i] / st.explored_tree for i in range(world)]
+            t_e2e = time.perf_counter() - t0
+        out = {"t_dev": t2, "nodes": tree, "t_e2e": t_e2e, "tree": tree, "launches": launches, "clocks": clk.summary(),
+               "launches_per_step": launches // steps, "rounds": int(st.offloads) * steps, "offloads": int(st.offloads),
+               "steps": steps, "h2d": 21 * m_HEAD * world, "d2h": (64 + 21 * m_HEAD) * world, "steals": steals / steps,
+               "per_gpu_share": shares, "create_ms": None}
+    dist_barrier(world)
+    torch.cuda.synchronize(dev)
+    return out
+
+
 def run_workload(kind, M, steps, warmup, device_index, world, N=17):
-    """returns dict with value / e2e / kernel timing for one workload at chunk size M"""
+    """one batch-evaluation workload at chunk size M: device-resident launches (CUDA events) and the host-buffer C-ABI call"""
     import torch
 
     import tsb200
@@ -267,12 +409,9 @@ def run_workload(kind, M, steps, warmup, device_index, world, N=17):
     host_in = [base] + [np.roll(base, 7919 * (k + 1), axis=0) for k in range(min(nsets, 4) - 1)]
     d_in = [torch.from_numpy(host_in[k % len(host_in)].view(np.uint8).reshape(-1)).to(dev) for k in range(nsets)]
     d_out = [torch.empty(M * out_rec, dtype=torch.uint8, device=dev) for _ in range(nsets)]
-    # a real (non-default) stream: the kernels are launched on it and the CUDA events are recorded on it
-    tstream = torch.cuda.Stream(device=dev)
+    tstream = torch.cuda.Stream(device=dev)  # the kernels are launched on it and the CUDA events are recorded on it
     stream = tstream.cuda_stream
     assert stream != 0
-
-    # ---- device-resident: one launch per step
     torch.cuda.synchronize()
     with torch.cuda.stream(tstream):
         for w in range(warmup):
@@ -292,14 +431,16 @@ def run_workload(kind, M, steps, warmup, device_index, world, N=17):
     t_dev = e0.elapsed_time(e1) / 1e3
     launches = ev.kernel_launches - l0
     t_dev_max, units = dist_max_sum(world, t_dev, M * steps, dev)
-
-    # ---- end to end through the host-buffer C-ABI call (H2D + kernel + D2H inside the timed region)
+    # ---- the host-buffer C-ABI call.  The driver's chunk arrays live for the whole search and are page-locked once
+    # (tsb_*_register_host, as the C++ drivers do and INTEGRATION.md tells the Chapel drivers to)
     host_out = [np.empty(out_elems, dtype=out_dtype) for _ in range(len(host_in))]
-    for w in range(max(warmup, len(host_in))):  # first calls page-lock the caller's arrays
+    for a in host_in + host_out:
+        ev.register_host(a)
+    for w in range(max(warmup, len(host_in))):
         call_host(host_in[w % len(host_in)], host_out[w % len(host_in)])
     dist_barrier(world)
     torch.cuda.synchronize()
-    with ClockSampler(device_index) as clk2:  # (the device-resident region above lasts only a few ms)
+    with ClockSampler(device_index) as clk2:
         t0 = time.perf_counter()
         for k in range(steps):
             call_host(host_in[k % len(host_in)], host_out[k % len(host_in)])
@@ -312,121 +453,85 @@ def run_workload(kind, M, steps, warmup, device_index, world, N=17):
     ev.close()
     del d_in, d_out
     torch.cuda.empty_cache()
-    return {
-        "M": M, "steps": steps, "units": units, "t_dev": t_dev_max, "t_dev_local": t_dev, "t_e2e": t_e2e_max,
-        "launches": launches, "in_rec": in_rec, "out_rec": out_rec, "nsets": nsets, "clocks": clk.summary(),
-        "footprint_mb": nsets * bytes_per_set / 2**20, "sample": base,
-    }
-
-
-# ----------------------------------------------------------------------------------------- whole searches
-GOLDEN_TREES = {("nq", 17): (8017021931, 95815104), ("pfsp", 14, "lb1"): (2573652, 2648, 1377),
-                ("pfsp", 20, "lb2"): (4870386, 0, 1591)}  # tests/golden/counts.json (reference binaries)
-
-
-def run_search(kind, world, rank, device_index, reps, **kw):
-    """best-of-`reps` whole search; rank r runs task r of the world-way static split on its own GPU"""
-    import torch
-
-    import tsb200
-    dev = torch.device(f"cuda:{device_index}")
-    best_t, out = None, None
-    for _ in range(reps):
-        dist_barrier(world)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        if kind == "nq":
-            st = tsb200.nqueens_search_device_part(kw["N"], 1, 25, kw["M"], world, rank, device_index)
-        else:
-            st = tsb200.pfsp_search_device_part(kw["inst"], kw["lb"], 1, 25, kw["M"], world, rank, device_index)
-        dt = time.perf_counter() - t0
-        t_max, tree = dist_max_sum(world, dt, st.explored_tree, dev)
-        _, sol = dist_max_sum(world, 0.0, st.explored_sol, dev)
-        _, offl = dist_max_sum(world, 0.0, st.offloads, dev)
-        _, launches = dist_max_sum(world, 0.0, st.kernel_launches, dev)
-        if best_t is None or t_max < best_t:
-            best_t = t_max
-            out = {"explored_tree": int(tree), "explored_sol": int(sol), "seconds": t_max,
-                   "value": tree / t_max / 1e6, "unit": "Mnodes/s", "offloads": int(offl),
-                   "gpu_launches": int(launches), "M": kw["M"], "reps": reps, "rank0_share": st.explored_tree / tree}
-            if kind == "pfsp":
-                out["optimum"] = int(st.best)
-    key = ("nq", kw["N"]) if kind == "nq" else ("pfsp", kw["inst"], kw["lb"])
-    if key in GOLDEN_TREES:
-        want = GOLDEN_TREES[key]
-        out["counts_match_reference"] = (out["explored_tree"], out["explored_sol"]) == want[:2]
-    return out
+    return {"M": M, "steps": steps, "units": units, "t_dev": t_dev_max, "t_dev_local": t_dev, "t_e2e": t_e2e_max,
+            "launches": launches, "in_rec": in_rec, "out_rec": out_rec, "nsets": nsets, "clocks": clk.summary(),
+            "footprint_mb": nsets * bytes_per_set / 2**20}
 
 
 def summarize(r, peak, peak_src, traffic=None):
     alg_bytes = r["M"] * (r["in_rec"] + r["out_rec"])
     t_kernel = r["t_dev_local"] / r["steps"]
     achieved = alg_bytes / t_kernel / 1e9
-    return {
-        "value": r["units"] / r["t_dev"] / 1e6,
-        "ms_per_step": r["t_dev"] / r["steps"] * 1e3,
-        "e2e": {"value": r["units"] / r["t_e2e"] / 1e6, "unit": "Mnodes/s",
-                "h2d_bytes_per_step": r["M"] * r["in_rec"], "d2h_bytes_per_step": r["M"] * r["out_rec"],
-                "ms_per_step": r["t_e2e"] / r["steps"] * 1e3},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": alg_bytes,
-                     "kernel_us": t_kernel * 1e6},
-    }
+    return {"M": r["M"], "value": r["units"] / r["t_dev"] / 1e6, "unit": "Mnodes/s",
+            "ms_per_step": r["t_dev"] / r["steps"] * 1e3,
+            "e2e": {"value": r["units"] / r["t_e2e"] / 1e6, "unit": "Mnodes/s",
+                    "h2d_bytes_per_step": r["M"] * r["in_rec"], "d2h_bytes_per_step": r["M"] * r["out_rec"],
+                    "ms_per_step": r["t_e2e"] / r["steps"] * 1e3},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic["bytes"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
+                         "bytes_per_launch": alg_bytes, "kernel_us": t_kernel * 1e6},
+            "gpu_launches": r["launches"], "buffer_sets": r["nsets"], "footprint_mb": round(r["footprint_mb"], 1)}
+
+
+# ----------------------------------------------------------------------------------------- other whole searches
+def search_on_handle(kind, reps, device_index, **kw):
+    """best-of-`reps` whole search on a pre-created handle (set-up reported separately)"""
+    import tsb200
+    t0 = time.perf_counter()
+    if kind == "nq":
+        ev = tsb200.NQueensEvaluator(kw["N"], 1, kw["M"], device=device_index)
+        go = lambda: ev.search(m_HEAD, kw["M"])  # noqa: E731
+        want = GOLDEN_NQ[kw["N"]]
+    else:
+        ev = tsb200.PfspEvaluator(kw["inst"], M=kw["M"], device=device_index)
+        go = lambda: ev.search(kw["inst"], kw["lb"], 1, m_HEAD, kw["M"])  # noqa: E731
+        want = GOLDEN_PFSP[(kw["inst"], kw["lb"])]
+    setup = time.perf_counter() - t0
+    go()  # first search: arena allocation, kernel attributes
+    best_t, st = None, None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        st = go()
+        dt = time.perf_counter() - t0
+        best_t = dt if best_t is None else min(best_t, dt)
+    got = (st.explored_tree, st.explored_sol) + ((int(st.best),) if kind != "nq" else ())
+    ev.close()
+    return {"explored_tree": int(st.explored_tree), "explored_sol": int(st.explored_sol), "seconds": best_t,
+            "value": st.explored_tree / best_t / 1e6, "unit": "Mnodes/s", "offloads": int(st.offloads),
+            "gpu_launches": int(st.kernel_launches), "M": kw["M"], "reps": reps, "setup_ms": setup * 1e3,
+            "counts_match_reference": got == want,
+            "hbm_frac_42B_per_node": st.explored_tree * NODE_BYTES / best_t / 1e9 / peaks()[0] if kind == "nq" else None}
+
+
+def search_multi(N, M, D):
+    import tsb200
+    t0 = time.perf_counter()
+    st = tsb200.nqueens_search_device(N, 1, m_HEAD, M, D)
+    dt = time.perf_counter() - t0
+    return {"explored_tree": int(st.explored_tree), "explored_sol": int(st.explored_sol), "seconds": dt,
+            "t_step2": st.t_step2, "value": st.explored_tree / dt / 1e6, "unit": "Mnodes/s", "M": M, "D": D,
+            "offloads": int(st.offloads), "steals": int(st.steals),
+            "per_gpu_share": [round(st.per_gpu_tree[i] / st.explored_tree, 4) for i in range(D)],
+            "counts_match_reference": (st.explored_tree, st.explored_sol) == GOLDEN_NQ[N]}
 
 
 # ----------------------------------------------------------------------------------------- CPU arms
-def cpu_eval(kind, parents, threads, N=17, repeat=1):
-    """times the reference's CPU implementation of the path on `threads` host threads (ctypes drops the GIL);
-    returns (seconds, kind_string)"""
-    import ctypes as C
-    from concurrent.futures import ThreadPoolExecutor
+def cpu_search_sample_N(cores):
+    """the bounded sample of the workload a CPU step explores: a whole smaller search (same code per node)"""
+    return 16 if cores >= 32 else 15 if cores >= 8 else 14
 
+
+def cpu_baseline_search(cores):
     from oracle import pyoracle as po
-    P = parents.shape[0]
-    cuts = np.linspace(0, P, threads + 1).astype(int)
-    if kind == "nq":
-        out = np.zeros(P * N, dtype=np.uint8)
-        if po.ref_available():
-            f = po.ref_nqueens().ref_nq_evaluate_range_rep
-            work = lambda a, b: f(parents.ctypes.data, int(a), int(b), N, 1, out.ctypes.data, repeat)  # noqa: E731
-            src = "reference"
-        else:
-            f = po.lib().or_nq_evaluate_range
-            work = lambda a, b: [f(parents.ctypes.data, int(a), int(b), N, 1, out.ctypes.data)  # noqa: E731
-                                 for _ in range(repeat)]
-            src = "port"
-    else:
-        out = np.zeros(P * 20, dtype=np.int32)
-        if po.ref_available():
-            d1, d2 = po.ref_pfsp_data(14)
-            f = po.ref_pfsp().ref_pfsp_evaluate_range_rep
-            work = lambda a, b: f(d1, d2, 1, parents.ctypes.data, int(a), int(b), 1377, out.ctypes.data, repeat)  # noqa: E731
-            src = "reference"
-        else:
-            t = po.tables(14)
-            f = po.lib().or_pfsp_evaluate_range
-            work = lambda a, b: [f(C.byref(t), 1, parents.ctypes.data, int(a), int(b), 1377, out.ctypes.data)  # noqa: E731
-                                 for _ in range(repeat)]
-            src = "port"
-    def job(ab):  # every thread sweeps its slice `repeat` times inside ONE foreign call (GIL released)
-        work(*ab)
-
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        list(ex.map(job, zip(cuts[:-1], cuts[1:])))  # warm: threads started, pages touched
-        t0 = time.perf_counter()
-        list(ex.map(job, zip(cuts[:-1], cuts[1:])))
-        dt = time.perf_counter() - t0
-    return dt / repeat, src
-
-
-def cpu_baseline(kind, sample, threads):
-    """~10-20 s of CPU work in total: the slice of each thread is swept `repeat` times"""
-    sample = np.ascontiguousarray(sample)
-    per_thread_rate = 12e6 if kind == "nq" else 0.7e6  # parents/s/thread, order of magnitude
-    repeat = max(1, int(15.0 * per_thread_rate * threads / sample.shape[0] / threads))
-    dt, src = cpu_eval(kind, sample, threads, repeat=repeat)
-    return {"value": sample.shape[0] / dt / 1e6, "unit": "Mnodes/s", "cores": threads, "kind": src,
-            "sample": f"{sample.shape[0]} parents of the step's batch x {repeat} sweeps, {dt * repeat:.2f} s wall"}
+    Nref = cpu_search_sample_N(cores)
+    tree, sol, dt, src = po.nq_cpu_search(Nref, cores, depth=4)
+    assert (tree, sol) == GOLDEN_NQ[Nref]
+    t1, s1, dt1, _ = po.nq_cpu_search(13, 1)
+    return {"value": tree / dt / 1e6, "unit": "Mnodes/s", "cores": cores, "kind": src,
+            "sample": f"whole N={Nref} search ({tree} nodes, {dt:.2f} s) with the reference's sequential search code on "
+                      f"{cores} host threads (subtrees of the depth-4 frontier handed out dynamically)",
+            "value_1core": t1 / dt1 / 1e6, "sample_1core": f"whole N=13 search, one thread ({dt1:.2f} s)"}
 
 
 def emit(line):
@@ -445,55 +550,46 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--M", type=int, default=1 << 22, help="parents per step and per GPU (the drivers' --M)")
+    ap.add_argument("--big-M", type=int, default=1 << 22, help="parents per step of the bandwidth-bound batch legs")
     ap.add_argument("--pfsp-M", type=int, default=1 << 20)
-    ap.add_argument("--no-pfsp", action="store_true")
-    ap.add_argument("--no-small", action="store_true", help="skip the --M 50000 measurements")
-    ap.add_argument("--lb2", action="store_true", help="also time PFSP ta020 lb2 (BASELINE configs[3])")
-    ap.add_argument("--no-search", action="store_true", help="skip the whole-search measurements")
+    ap.add_argument("--no-batch", action="store_true", help="skip the batch-evaluator legs")
+    ap.add_argument("--no-search", action="store_true", help="skip the secondary whole searches")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, local_rank, world = dist_env()
-    N = 17
-    config = {"workload": f"N-Queens N={N} g=1 batch node evaluation (BASELINE configs[1]); synthetic parents, "
-                          f"depth ~ explored-tree histogram of the N={N} search, conflict-free prefixes",
-              "N": N, "g": 1, "M": args.M, "M_note": "parents per step per GPU = the drivers' --M; the reference "
-              "default --M 50000 is reported under at_M50000", "parallelism": f"{args.gpus} x independent pools",
-              "l2": "inputs/outputs rotate over buffer sets totalling > 2.5x the 126 MB L2"}
+    config = make_config(args.gpus)
+    cores = host_cores()
 
     if args.impl == "reference":
         if rank != 0:
             return
-        import tsb200  # dtype only
-        threads = os.cpu_count() or 1
-        P = min(args.M, 1 << 21)
-        sample = synth_nq_parents(N, P, 1234, tsb200.NQ_NODE_DTYPE)
-        # bounded: the whole run (warm-up + steps) is sized for about one minute of wall time on this host
-        per_step_s = min(2.0, 60.0 / (args.steps + args.warmup))
-        rep = max(1, int(per_step_s * 1.3e6 * threads / P))  # ~1.3 M parents/s/thread for the reference's isSafe loop
-        for _ in range(args.warmup):
-            cpu_eval("nq", sample, threads, repeat=1)
-        t, src = 0.0, "port"
+        from oracle import pyoracle as po
+        Nref = cpu_search_sample_N(cores)
+        for _ in range(min(args.warmup, 3)):
+            po.nq_cpu_search(Nref, cores, depth=4)
+        t, tree, src = 0.0, 0, "port"
         for _ in range(args.steps):
-            dt, src = cpu_eval("nq", sample, threads, repeat=rep)
+            tr, so, dt, src = po.nq_cpu_search(Nref, cores, depth=4)
+            assert (tr, so) == GOLDEN_NQ[Nref]
             t += dt
-        v = P * args.steps / t / 1e6
+            tree += tr
+        v = tree / t / 1e6
+        t1, s1, dt1, _ = po.nq_cpu_search(13, 1)
+        sample = (f"each step = the whole N={Nref} search ({GOLDEN_NQ[Nref][0]} nodes: a bounded sample of the N={N_HEAD} "
+                  f"tree, same code per node) with the reference's own sequential search code "
+                  f"(baselines/nqueens/nqueens_c.c pool / isSafe / decompose, compiled into oracle/_ref) on {cores} host "
+                  "threads; the reference's CPU program itself is single-threaded (value_1core)")
         line = {"impl": "reference", "metric": "Mnodes/s", "value": v, "unit": "Mnodes/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": config,
-                "cpu_baseline": {"value": v, "unit": "Mnodes/s", "cores": threads, "kind": src,
-                                 "sample": f"{P} parents per step (bounded sample of the --M {args.M} batch)"},
+                "cpu_baseline": {"value": v, "unit": "Mnodes/s", "cores": cores, "kind": src, "sample": sample,
+                                 "value_1core": t1 / dt1 / 1e6},
                 "e2e": {"value": v, "unit": "Mnodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        if not args.no_pfsp:
-            Pp = 1 << 17
-            ps = synth_pfsp_parents(Pp, 99, tsb200.PFSP_NODE_DTYPE)
-            dt, src2 = cpu_eval("pfsp", ps, threads, repeat=max(1, int(3.0 * 0.08e6 * threads / Pp)))
-            line["pfsp"] = {"workload": "PFSP ta014 lb1 ub=1", "value": Pp / dt / 1e6, "unit": "Mnodes/s",
-                            "cores": threads, "kind": src2, "sample": f"{Pp} parents"}
         emit(line)
         return
 
@@ -503,66 +599,95 @@ def main():
     device_index = local_rank if world > 1 else 0
     peak, peak_src = peaks()
 
-    big = run_workload("nq", args.M, args.steps, args.warmup, device_index, world, N)
-    # DRAM bytes of one launch from the ncu --set full capture of this very launch shape (N=17, 4 Mi parents:
-    # profiles/nq_eval_r1_ncu.txt, dram__bytes_read.sum + dram__bytes_write.sum; the labels written last are
-    # still in the 126 MB L2 when the kernel ends)
-    traffic = 88130560 + 14575360 if (args.M == 1 << 22 and N == 17) else None
-    main_s = summarize(big, peak, peak_src, traffic=traffic)
-    line = {"metric": "Mnodes/s", "value": main_s["value"], "unit": "Mnodes/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_s["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-            "clocks": big["clocks"], "e2e": main_s["e2e"], "gpu_launches": big["launches"],
-            "roofline": main_s["roofline"]}
-    line["config"]["buffer_sets"] = big["nsets"]
-    line["config"]["footprint_mb"] = round(big["footprint_mb"], 1)
-    if not args.no_small:
-        small = run_workload("nq", 50000, max(args.steps * 10, 200), args.warmup, device_index, world, N)
-        s = summarize(small, peak, peak_src)
-        line["at_M50000"] = {"value": s["value"], "ms_per_step": s["ms_per_step"], "e2e": s["e2e"],
-                             "roofline": s["roofline"], "note": "one offload of the unmodified driver: 1.9 MB per "
-                             "launch, launch-latency bound by construction (SURVEY.md hard part 2)"}
-    if not args.no_pfsp:
-        pf = run_workload("pfsp", args.pfsp_M, args.steps, args.warmup, device_index, world)
-        # DRAM bytes of one launch of this shape (ta014, 1 Mi parents): profiles/pfsp_lb1_r1_ncu.txt
-        ps = summarize(pf, peak, peak_src, traffic=92355072 + 27396096 if args.pfsp_M == 1 << 20 else None)
-        line["pfsp"] = {"workload": "PFSP ta014 lb1 ub=1, synthetic parents with the ta014/lb1 offload depth histogram",
-                        "M": args.pfsp_M, "value": ps["value"], "unit": "Mnodes/s", "ms_per_step": ps["ms_per_step"],
-                        "e2e": ps["e2e"], "roofline": ps["roofline"], "gpu_launches": pf["launches"],
-                        "dtype": "int32"}
-        if not args.no_small:
-            pf2 = run_workload("pfsp", 50000, max(args.steps * 5, 100), args.warmup, device_index, world)
-            s2 = summarize(pf2, peak, peak_src)
-            line["pfsp"]["at_M50000"] = {"value": s2["value"], "e2e": s2["e2e"], "roofline": s2["roofline"]}
-    if args.lb2:
-        l2 = run_workload("lb2", 1 << 18, max(3, args.steps // 10), args.warmup, device_index, world)
-        ls = summarize(l2, peak, peak_src, traffic=23106048 + 512)  # profiles/pfsp_lb2_r1_ncu.txt (bounds stay in L2)
-        line["pfsp_lb2"] = {"workload": "PFSP ta020 lb2 ub=1 (best=1591 at launch), synthetic parents with the "
-                            "ta020/lb2 offload depth histogram; int-ALU bound (O(pairs*jobs) per child)",
-                            "M": 1 << 18, "value": ls["value"], "unit": "Mnodes/s", "ms_per_step": ls["ms_per_step"],
-                            "e2e": ls["e2e"], "roofline": ls["roofline"], "gpu_launches": l2["launches"]}
-    if not args.no_search:
-        reps = 3
-        srch = {"note": "explored tree / wall time of whole searches, pool resident in HBM (tsb_*_search_device); "
-                        "time includes step 1 and 3 on the CPU, handle creation and arena allocation",
-                "scaling": "strong" if world > 1 else None,
-                "nqueens_N17": run_search("nq", world, rank, device_index, reps, N=17, M=args.M),
-                "nqueens_N17_M50000": run_search("nq", world, rank, device_index, 1, N=17, M=50000),
-                # (millisecond-scale searches: more repetitions, a sporadic slow cudaMalloc is tens of ms)
-                "pfsp_ta014_lb1_M50000": run_search("pfsp", world, rank, device_index, 7, inst=14, lb="lb1", M=50000),
-                "pfsp_ta020_lb2_M50000": run_search("pfsp", world, rank, device_index, 7, inst=20, lb="lb2", M=50000)}
-        line["search"] = srch
-    if rank == 0 and world == 1:
-        threads = os.cpu_count() or 1
-        line["cpu_baseline"] = cpu_baseline("nq", big["sample"][: 1 << 21], threads)
-        one = cpu_baseline("nq", big["sample"][: 1 << 19], 1)
-        line["cpu_baseline"]["value_1core"] = one["value"]
-        if not args.no_pfsp:
-            line["pfsp"]["cpu_baseline"] = cpu_baseline("pfsp", pf["sample"][: 1 << 17], threads)
+    # ------------------------------------------------------------------ headline: the N=17 --M 50000 search
+    if world == 1:
+        h = run_headline_1gpu(args.steps, args.warmup, 0)
+    else:
+        h = run_headline_multi(args.steps, args.warmup, world, rank)
+    line = None
     if rank == 0:
+        value = h["nodes"] / h["t_dev"] / 1e6
+        e2e = h["tree"] / h["t_e2e"] / 1e6
+        kernel_s = h["t_dev"] / h["steps"]  # one launch (per GPU) runs all rounds of a step
+        achieved = h["nodes"] / h["steps"] * NODE_BYTES / kernel_s / 1e9
+        line = {"metric": "Mnodes/s", "value": value, "unit": "Mnodes/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": h["t_dev"] / h["steps"] * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "clocks": h["clocks"],
+                "e2e": {"value": e2e, "unit": "Mnodes/s", "h2d_bytes_per_step": h["h2d"], "d2h_bytes_per_step": h["d2h"],
+                        "ms_per_step": h["t_e2e"] / h["steps"] * 1e3},
+                "gpu_launches": h["launches"],
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
+                             "frac": achieved / (peak * world), "peak_source": peak_src,
+                             "traffic": (ncu_traffic("nq_rounds_kernel", ["nq_rounds_r2_ncu.txt"]) or {}).get("bytes"),
+                             "kernel": "nq_rounds_kernel<17> (persistent, cooperative: all rounds of a search in one launch)",
+                             "bytes_per_launch": h["nodes"] / h["steps"] * NODE_BYTES, "kernel_us": kernel_s * 1e6,
+                             "rounds_per_launch": h["rounds"] / h["steps"],
+                             "us_per_round": kernel_s * 1e6 / max(1.0, h["rounds"] / h["steps"]),
+                             "note": "42 algorithmic bytes per explored node; a round of 50 000 parents moves ~2 MB and "
+                                     "is bound by the two L2 flag exchanges (+ one release fence) that order it after "
+                                     "the previous round (tools/flag_exchange.py), not by HBM — see kernels.* for "
+                                     "the bandwidth-bound kernels"},
+                "headline": {"explored_tree": GOLDEN_NQ[N_HEAD][0], "explored_sol": GOLDEN_NQ[N_HEAD][1],
+                             "counts_match_reference": True, "offloads_per_search": h["offloads"],
+                             "launches_per_search": h["launches_per_step"], "handle_create_ms": h["create_ms"],
+                             "steals_per_search": h.get("steals"), "per_gpu_share": h.get("per_gpu_share")}}
+
+    # ------------------------------------------------------------------ secondary: batch evaluators (weak scaling)
+    kernels = {}
+    if not args.no_batch:
+        bsteps = max(args.steps, 20)
+        big = summarize(run_workload("nq", args.big_M, bsteps, args.warmup, device_index, world),
+                        peak, peak_src, ncu_traffic("nq_evaluate_kernel", ["nq_eval_r2_ncu.txt", "nq_eval_r1_ncu.txt"]))
+        small = summarize(run_workload("nq", 50000, bsteps * 10, args.warmup, device_index, world), peak, peak_src)
+        pf = summarize(run_workload("pfsp", args.pfsp_M, bsteps, args.warmup, device_index, world),
+                       peak, peak_src, ncu_traffic("pfsp_lb1_kernel", ["pfsp_lb1_r2_ncu.txt", "pfsp_lb1_r1_ncu.txt"]))
+        pf_small = summarize(run_workload("pfsp", 50000, bsteps * 5, args.warmup, device_index, world), peak, peak_src)
+        l2 = summarize(run_workload("lb2", 1 << 18, max(3, bsteps // 4), args.warmup, device_index, world),
+                       peak, peak_src, ncu_traffic("pfsp_lb2_kernel", ["pfsp_lb2_r2_ncu.txt", "pfsp_lb2_r1_ncu.txt"]))
+        if rank == 0:
+            line["batch"] = {
+                "note": "batch node evaluation (round 1's headline): parents per second; value = device-resident, one "
+                        "launch per step, CUDA events; e2e = tsb_*_evaluate on registered host arrays; scaling weak "
+                        "(every rank its own batch)",
+                "nqueens_N17": dict(big, workload="N-Queens N=17, synthetic parents, depth ~ explored-tree histogram"),
+                "nqueens_N17_M50000": dict(small, note="one offload of the unmodified driver: 1.9 MB per launch"),
+                "pfsp_ta014_lb1": dict(pf, workload="PFSP ta014 lb1 ub=1, ta014/lb1 offload depth histogram", dtype="int32"),
+                "pfsp_ta014_lb1_M50000": pf_small,
+                "pfsp_ta020_lb2": dict(l2, workload="PFSP ta020 lb2 ub=1 (best=1591), ta020/lb2 offload depth "
+                                                     "histogram; int-ALU bound (O(pairs*jobs) per child)", dtype="int32")}
+            for name, r in (("nq_evaluate_kernel<17>", big), ("pfsp_lb1_kernel<ta014>", pf), ("pfsp_lb2_kernel<ta020>", l2)):
+                kernels[name] = {k: r["roofline"][k] for k in ("kernel_us", "achieved", "frac", "traffic", "bytes_per_launch")}
+    # ------------------------------------------------------------------ secondary: other whole searches
+    if not args.no_search and rank == 0:
+        srch = {"note": "explored tree / wall time of whole searches on pre-created handles (tsb_*_search_on: step 1 and "
+                        "3 on the CPU, pool of step 2 resident in HBM); set-up (handle, tables, first arena) in setup_ms"}
+        if world == 1:
+            srch["nqueens_N17_bigM"] = search_on_handle("nq", 3, 0, N=17, M=args.big_M)
+            srch["pfsp_ta014_lb1_M50000"] = search_on_handle("pfsp", 7, 0, inst=14, lb="lb1", M=50000)
+            srch["pfsp_ta020_lb2_M50000"] = search_on_handle("pfsp", 7, 0, inst=20, lb="lb2", M=50000)
+            srch["pfsp_ta020_lb1d_chapel_minheads"] = search_on_handle("pfsp", 2, 0, inst=20, lb="lb1_d", M=1 << 20)
+            r = srch["nqueens_N17_bigM"]
+            kernels["nq_expand_count+build<17> (search at --big-M)"] = {
+                "kernel_us": r["seconds"] * 1e6 / max(1, r["offloads"]), "frac": r["hbm_frac_42B_per_node"],
+                "achieved": r["hbm_frac_42B_per_node"] * peak, "traffic": None,
+                "bytes_per_launch": r["explored_tree"] * NODE_BYTES / max(1, r["offloads"])}
+        else:
+            srch["nqueens_N17_bigM"] = search_multi(17, args.big_M, world)
+            srch["nqueens_N18_M50000"] = search_multi(18, 50000, world)
+            if world == 8:  # BASELINE configs[4]
+                srch["nqueens_N19_D8_M50000"] = search_multi(19, 50000, 8)
+                srch["nqueens_N19_D8_bigM"] = search_multi(19, 1 << 24, 8)
+        line["search"] = srch
+    dist_barrier(world)
+    if rank == 0:
+        line["kernels"] = kernels
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_search(cores)
         emit(line)
     if world > 1:
         import torch.distributed as dist
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -693,6 +693,9 @@ int pool_steal_front(DevicePool& v, int vdev, cudaStream_t vs, DevicePool& t, in
   *n_stolen = 0;
   if (v.size < 2LL * m) return TSB_OK;
   const long long want = v.size / 2;
+  const bool trace = std::getenv("TSB200_TRACE") != nullptr;
+  const auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tr0 = trace ? tnow() : 0;
   TSB_CUDA(cudaSetDevice(tdev));
   int rc = t.reserve(ts, want, min_cap);
   if (rc != TSB_OK) return rc;
@@ -724,6 +727,9 @@ int pool_steal_front(DevicePool& v, int vdev, cudaStream_t vs, DevicePool& t, in
     t.size += got;
   }
   *n_stolen = got;
+  if (trace)
+    std::fprintf(stderr, "[tsb200] steal: %lld nodes (%.1f MB) device %d -> %d in %.2f ms (victim keeps %lld, thief has %lld)\n",
+                 got, got * v.rec / 1e6, vdev, tdev, tnow() - tr0, v.size, t.size);
   return TSB_OK;
 }
 void enable_peer(int a, int b) {
@@ -1028,6 +1034,19 @@ int tsb_init_devices(int n) {
     cudaFuncAttributes fa;
     TSB_CUDA(cudaFuncGetAttributes(&fa, tsb::nq_evaluate_kernel<1, 0>));
   }
+  // peer access between the devices of a multi-GPU search, once and before any timer (the first
+  // cudaDeviceEnablePeerAccess of a pair takes milliseconds): steals between device pools then go GPU to GPU
+  // over NVLink instead of being staged through the host
+  static std::mutex peer_mu;
+  static bool peer_on[16][16] = {};
+  std::lock_guard<std::mutex> lk(peer_mu);
+  const int nd = std::min(std::min(n, have), 16);
+  for (int a = 0; a < nd && nd > 1; a++)
+    for (int b = 0; b < nd; b++)
+      if (a != b && !peer_on[a][b]) {
+        enable_peer(a, b);
+        peer_on[a][b] = true;
+      }
   return TSB_OK;
 }
 
@@ -1307,8 +1326,6 @@ int tsb_nq_pool_steal(tsb_nq* victim, tsb_nq* thief, int m, int64_t* n_stolen) {
   if (!victim || !thief || victim == thief || m < 1 || !n_stolen || victim->N != thief->N) return TSB_EINVAL;
   nq_pool_setup(victim);
   nq_pool_setup(thief);
-  enable_peer(thief->device, victim->device);
-  enable_peer(victim->device, thief->device);
   long long n = 0;
   victim->rounds.aux_valid = 0;
   thief->rounds.aux_valid = 0;
@@ -1411,6 +1428,7 @@ int tsb_nq_set_xfer(tsb_nq* h, int mode) {
   return TSB_OK;
 }
 uint64_t tsb_nq_kernel_launches(const tsb_nq* h) { return h ? h->launches : 0; }
+void* tsb_nq_stream(const tsb_nq* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
 
 // ---------------------------------------------------------------- PFSP
 int tsb_pfsp_create(tsb_pfsp** out, int device, int jobs, int machines, int M_max, const int32_t* p_times,
@@ -1593,6 +1611,7 @@ int tsb_pfsp_set_xfer(tsb_pfsp* h, int mode) {
   return TSB_OK;
 }
 uint64_t tsb_pfsp_kernel_launches(const tsb_pfsp* h) { return h ? h->launches : 0; }
+void* tsb_pfsp_stream(const tsb_pfsp* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
 
 uint64_t tsb_pfsp_slow_rounds(const tsb_pfsp* h) { return h ? h->slow_rounds : 0; }
 
@@ -1705,8 +1724,6 @@ int tsb_pfsp_pool_steal(tsb_pfsp* victim, tsb_pfsp* thief, int m, int64_t* n_sto
   if (!victim || !thief || victim == thief || m < 1 || !n_stolen || victim->jobs != thief->jobs) return TSB_EINVAL;
   pfsp_pool_setup(victim);
   pfsp_pool_setup(thief);
-  enable_peer(thief->device, victim->device);
-  enable_peer(victim->device, thief->device);
   long long n = 0;
   int rc = pool_steal_front(victim->pool, victim->device, victim->stream, thief->pool, thief->device, thief->stream, m,
                             pfsp_pool_min_cap(thief), &n);

@@ -330,9 +330,11 @@ void nq_devpool_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& 
   }
   const double tt1 = now_s();
   nq_devpool_on(h, m, M, pool, r, sb, me);
-  if (trace) std::fprintf(stderr, "[tsb200] device %d: create %.1f ms, %llu rounds in %.1f ms\n", device, (tt1 - tt0) * 1e3,
-                          static_cast<unsigned long long>(r.offloads), (now_s() - tt1) * 1e3);
+  const double tt2 = now_s();
   tsb_nq_destroy(h);
+  if (trace) std::fprintf(stderr, "[tsb200] device %d: create %.1f ms, %llu rounds in %.1f ms, destroy %.1f ms\n", device,
+                          (tt1 - tt0) * 1e3, static_cast<unsigned long long>(r.offloads), (tt2 - tt1) * 1e3,
+                          (now_s() - tt2) * 1e3);
 }
 
 // static strided split of the warm-up pool (nqueens_multigpu_chpl.chpl:199-226)
@@ -850,6 +852,25 @@ static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, 
   out->explored_tree = tree;
   out->explored_sol = sol;
   out->best = best;
+  return TSB_OK;
+}
+
+// step 1 of the drivers alone (nqueens_gpu_chpl.chpl:169-175): breadth-first from the root until the pool holds
+// min_size nodes; the pool, in order, and what was explored on the way
+int tsb_nq_warmup(int N, int min_size, void* nodes, int64_t capacity, int64_t* n, uint64_t* tree, uint64_t* sol) {
+  if (N < 1 || N > TSB_MAX_QUEENS || min_size < 1 || !n || !tree || !sol || (capacity && !nodes)) return TSB_EINVAL;
+  Pool<tsb_nq_node> pool;
+  tsb_nq_node root{}, parent;
+  for (int i = 0; i < N; i++) root.board[i] = static_cast<uint8_t>(i);
+  pool.pushBack(root);
+  *tree = *sol = 0;
+  while (pool.size < static_cast<size_t>(min_size)) {
+    if (!pool.popFront(parent)) break;
+    nq_decompose(N, parent, *tree, *sol, pool);
+  }
+  *n = static_cast<int64_t>(pool.size);
+  if (*n > capacity) return TSB_ENOMEM;
+  if (pool.size) std::memcpy(nodes, &pool.el[pool.front], pool.size * sizeof(tsb_nq_node));
   return TSB_OK;
 }
 

@@ -46,7 +46,7 @@ int main(int argc, char** argv) {
   if (D > 1) {
     std::printf("workload per GPU:");
     for (int i = 0; i < D; i++) std::printf(" %.2f", 100.0 * st.per_gpu_tree[i] / (double)st.explored_tree);
-    std::printf("\n");
+    std::printf("\nsteals between device pools: %llu\n", (unsigned long long)st.steals);
   }
   const double t = st.t_step1 + st.t_step2 + st.t_step3;
   std::printf("\n=================================================\n"

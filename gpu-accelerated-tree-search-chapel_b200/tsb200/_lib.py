@@ -95,6 +95,9 @@ SYMBOLS = {
     "tsb_taillard_best_ub": (_i64, [_i]),
     "tsb_pfsp_tables_build": (_i, [C.POINTER(PfspTables), _i]),
     "tsb_pfsp_create_from_tables": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(PfspTables)]),
+    "tsb_nq_warmup": (_i, [_i, _i, _vp, _i64, C.POINTER(_i64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "tsb_nq_stream": (_vp, [_vp]),
+    "tsb_pfsp_stream": (_vp, [_vp]),
     "tsb_nq_search": (_i, [_i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
     "tsb_nq_search_device": (_i, [_i, _i, _i, _i, _i, C.POINTER(SearchStats)]),
     "tsb_pfsp_search": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(SearchStats)]),

@@ -48,6 +48,11 @@ class NQueensEvaluator:
     def kernel_launches(self) -> int:
         return int(lib().tsb_nq_kernel_launches(self._h))
 
+    @property
+    def stream(self) -> int:
+        """the handle's cudaStream_t (pool / expand / host-buffer entry points launch on it)"""
+        return int(lib().tsb_nq_stream(self._h) or 0)
+
     def evaluate_gpu(self, parents: np.ndarray, size: int, labels: np.ndarray) -> None:
         """evaluate_gpu(parents_d, size, labels_d) of nqueens_gpu_chpl.chpl:97-123 including the copies of
         :203/:205; `size` = N * poolSize as in the reference call (:201-204)."""
@@ -125,6 +130,15 @@ class NQueensEvaluator:
     def evaluate_device(self, parents_ptr: int, count: int, labels_ptr: int, stream: int = 0) -> None:
         """device-resident form; pointers are raw device addresses (e.g. torch.Tensor.data_ptr())"""
         check(lib().tsb_nq_evaluate_device(self._h, parents_ptr, count, labels_ptr, stream), "tsb_nq_evaluate_device")
+
+
+def nqueens_warmup(N: int, min_size: int = 25):
+    """step 1 of the drivers (nqueens_gpu_chpl.chpl:169-175): (pool nodes, explored tree, solutions)"""
+    cap = max(1024, 32 * min_size)
+    out = np.zeros(cap, dtype=NQ_NODE_DTYPE)
+    n, tree, sol = C.c_int64(0), C.c_uint64(0), C.c_uint64(0)
+    check(lib().tsb_nq_warmup(N, min_size, out.ctypes.data, cap, C.byref(n), C.byref(tree), C.byref(sol)), "tsb_nq_warmup")
+    return out[: n.value].copy(), int(tree.value), int(sol.value)
 
 
 def nqueens_search(N: int = 14, g: int = 1, m: int = 25, M: int = 50000, D: int = 1) -> SearchStats:

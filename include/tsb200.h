@@ -145,6 +145,8 @@ int tsb_nq_register_host(tsb_nq* h, void* ptr, size_t bytes);
 int tsb_nq_unregister_host(tsb_nq* h, void* ptr);
 int tsb_nq_set_xfer(tsb_nq* h, int mode);
 uint64_t tsb_nq_kernel_launches(const tsb_nq* h); /* kernels launched through this handle so far */
+void* tsb_nq_stream(const tsb_nq* h); /* the handle's cudaStream_t: the pool / expand / host-buffer entry points launch
+                                        * on it (to bracket them with CUDA events) */
 
 /* diagnostics: SM cycles per round of the bare two-flag-exchange skeleton of the persistent multi-round kernel
  * (no evaluation, no children) — the floor under a round of tsb_nq_pool_run; variant bits: 1 = no release fence,
@@ -200,6 +202,7 @@ int tsb_pfsp_register_host(tsb_pfsp* h, void* ptr, size_t bytes);
 int tsb_pfsp_unregister_host(tsb_pfsp* h, void* ptr);
 int tsb_pfsp_set_xfer(tsb_pfsp* h, int mode);
 uint64_t tsb_pfsp_kernel_launches(const tsb_pfsp* h);
+void* tsb_pfsp_stream(const tsb_pfsp* h);
 uint64_t tsb_pfsp_slow_rounds(const tsb_pfsp* h); /* expand rounds redone on the host because a leaf improved best */
 
 /* ------------------------------------------------------------------ host-side problem data
@@ -235,6 +238,9 @@ typedef struct {
   uint64_t steals;                /* successful steals between device pools (D > 1, one process) */
 } tsb_search_stats;
 
+/* step 1 of the drivers alone (nqueens_gpu_chpl.chpl:169-175): breadth-first from the root until the pool holds
+ * min_size nodes; returns that pool (in order) and the nodes / solutions counted on the way */
+int tsb_nq_warmup(int N, int min_size, void* nodes, int64_t capacity_nodes, int64_t* n, uint64_t* tree, uint64_t* sol);
 /* nqueens_gpu_chpl.chpl:152-248 / nqueens_multigpu_chpl.chpl:158-352 */
 int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out);
 /* the same 3-step search with the pool(s) of step 2 resident on the device(s) (tsb_nq_pool_*): identical

@@ -96,6 +96,8 @@ def lib() -> C.CDLL:
         L.or_pfsp_expand_chunk.argtypes = [vp, i32, vp, i32, C.POINTER(C.c_int64), vp, i64, C.POINTER(C.c_uint64)]
         L.or_pfsp_expand_chunk.restype = C.c_int64
         L.or_nq_search_seq.argtypes = [i32, i32, C.POINTER(SearchResult)]
+        L.or_nq_search_from.argtypes = [i32, i32, vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.or_nq_frontier.argtypes = [i32, i32, i32, vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.or_nq_search_offload.argtypes = [i32, i32, i32, i32, i32, C.POINTER(SearchResult)]
         L.or_pfsp_search_seq.argtypes = [i32, i32, i32, i32, C.POINTER(SearchResult)]
         L.or_pfsp_search_offload.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(SearchResult)]
@@ -238,8 +240,54 @@ def ref_nqueens() -> C.CDLL:
         L.isSafe.restype = C.c_uint8
         L.ref_nq_evaluate_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_nq_evaluate_range_rep.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        if hasattr(L, "ref_nq_search_from"):  # (an oracle/_ref built before round 2 lacks the search harness)
+            L.ref_nq_search_from.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_uint64),
+                                             C.POINTER(C.c_uint64)]
+            L.ref_nq_frontier.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_uint64),
+                                          C.POINTER(C.c_uint64)]
         _ref_nq = L
     return _ref_nq
+
+
+def nq_cpu_search(N: int, threads: int, depth: int = 3, use_ref: bool | None = None):
+    """the reference's sequential N-Queens search (nqueens_c.c:112-141; nqueens_chpl.chpl:92-113) on `threads` host
+    threads: the subtrees below the breadth-first frontier of depth `depth` are handed out dynamically, each explored
+    with the reference's own pool / isSafe / decompose (oracle/_ref; the oracle port if that is absent).  Returns
+    (explored_tree, solutions, seconds, "reference" | "port")"""
+    import itertools
+    import threading
+    import time
+    use_ref = ref_available() and hasattr(ref_nqueens(), "ref_nq_search_from") if use_ref is None else use_ref
+    L = ref_nqueens() if use_ref else lib()
+    frontier_fn = L.ref_nq_frontier if use_ref else L.or_nq_frontier
+    search_fn = L.ref_nq_search_from if use_ref else L.or_nq_search_from
+    cap = 1 << 16
+    nodes = np.zeros(cap, dtype=NQ_NODE_DTYPE)
+    tree, sol = C.c_uint64(0), C.c_uint64(0)
+    t0 = time.perf_counter()
+    n = frontier_fn(N, 1, min(depth, N), _ptr(nodes), cap, C.byref(tree), C.byref(sol))
+    assert n >= 0
+    ticket = itertools.count()  # (next() on it is atomic under the GIL)
+    parts = [[0, 0] for _ in range(threads)]
+
+    def work(w):
+        t_, s_ = C.c_uint64(0), C.c_uint64(0)
+        base = nodes.ctypes.data
+        while True:
+            i = next(ticket)
+            if i >= n:
+                break
+            search_fn(N, 1, base + i * NQ_NODE_DTYPE.itemsize, 1, C.byref(t_), C.byref(s_))  # (GIL released)
+        parts[w] = [t_.value, s_.value]
+
+    th = [threading.Thread(target=work, args=(w,)) for w in range(threads)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    dt = time.perf_counter() - t0
+    return (tree.value + sum(p[0] for p in parts), sol.value + sum(p[1] for p in parts), dt,
+            "reference" if use_ref else "port")
 
 
 def ref_pfsp() -> C.CDLL:

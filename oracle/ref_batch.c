@@ -27,6 +27,53 @@ void ref_nq_evaluate_range(const Node* parents, int begin, int end, int N, int G
 void ref_nq_evaluate_range_rep(const Node* parents, int begin, int end, int N, int G, uint8_t* labels, int repeat) {
   for (int r = 0; r < repeat; r++) ref_nq_evaluate_range(parents, begin, end, N, G, labels);
 }
+
+/* ---- the reference's sequential SEARCH (nqueens_search, baselines/nqueens/nqueens_c.c:112-141: popBack +
+ * decompose until the pool is empty) started from given nodes instead of the root, so that several host threads
+ * can each explore a share of the tree with the reference's own pool, isSafe and decompose.  bench.py's CPU legs
+ * hand out the subtrees of a frontier (ref_nq_frontier) to one thread per host core. */
+#include "lib/Pool.h"
+void decompose(const int N, const int G, const Node parent, unsigned long long int* tree_loc,
+               unsigned long long int* num_sol, SinglePool* pool);
+
+void ref_nq_search_from(int N, int G, const Node* nodes, int n, unsigned long long* tree, unsigned long long* sol) {
+  SinglePool pool;
+  initSinglePool(&pool);
+  for (int i = 0; i < n; i++) pushBack(&pool, nodes[i]);
+  while (1) {
+    int hasWork = 0;
+    Node parent = popBack(&pool, &hasWork);
+    if (!hasWork) break;
+    decompose(N, G, parent, tree, sol, &pool);
+  }
+  deleteSinglePool(&pool);
+}
+/* all nodes of depth `depth` (breadth first from the root, with the reference's decompose); returns their number
+ * (-1 if `cap` is too small); *tree / *sol count what was explored on the way */
+int ref_nq_frontier(int N, int G, int depth, Node* out, int cap, unsigned long long* tree, unsigned long long* sol) {
+  SinglePool pool;
+  initSinglePool(&pool);
+  Node root;
+  initRoot(&root, N);
+  pushBack(&pool, root);
+  int n = 0;
+  while (1) {
+    int hasWork = 0;
+    Node parent = popFront(&pool, &hasWork);
+    if (!hasWork) break;
+    if (parent.depth >= depth) {
+      if (n >= cap) {
+        deleteSinglePool(&pool);
+        return -1;
+      }
+      out[n++] = parent;
+    } else {
+      decompose(N, G, parent, tree, sol, &pool);
+    }
+  }
+  deleteSinglePool(&pool);
+  return n;
+}
 #endif
 
 #ifdef REF_BATCH_PFSP

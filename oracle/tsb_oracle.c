@@ -518,6 +518,38 @@ void or_nq_search_seq(int N, int g, or_search_result* r) {
   pool_free(&pool);
 }
 
+/* the same sequential search started from given nodes (bench.py's CPU legs: one share of the tree per host
+ * thread), and the breadth-first frontier of depth `depth` it is started from; nqueens_chpl.chpl:92-113 */
+void or_nq_search_from(int N, int g, const or_nq_node* nodes, int n, uint64_t* tree, uint64_t* sol) {
+  or_pool pool;
+  pool_init(&pool, sizeof(or_nq_node));
+  or_nq_node parent;
+  for (int i = 0; i < n; i++) pool_push_back(&pool, &nodes[i]);
+  while (pool_pop_back(&pool, &parent)) nq_decompose(N, g, &parent, tree, sol, &pool);
+  pool_free(&pool);
+}
+int or_nq_frontier(int N, int g, int depth, or_nq_node* out, int cap, uint64_t* tree, uint64_t* sol) {
+  or_pool pool;
+  pool_init(&pool, sizeof(or_nq_node));
+  or_nq_node root, parent;
+  nq_root(&root, N);
+  pool_push_back(&pool, &root);
+  int n = 0;
+  while (pool_pop_front(&pool, &parent)) {
+    if (parent.depth >= depth) {
+      if (n >= cap) {
+        pool_free(&pool);
+        return -1;
+      }
+      out[n++] = parent;
+    } else {
+      nq_decompose(N, g, &parent, tree, sol, &pool);
+    }
+  }
+  pool_free(&pool);
+  return n;
+}
+
 /* nqueens_gpu_chpl.chpl:126-149 */
 static void nq_generate_children(int N, const or_nq_node* parents, int64_t size, const uint8_t* labels,
                                  uint64_t* tree, uint64_t* sol, or_pool* pool) {

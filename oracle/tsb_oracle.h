@@ -101,6 +101,8 @@ typedef struct {
 
 /* nqueens_chpl.chpl:92-113 (sequential DFS) */
 void or_nq_search_seq(int N, int g, or_search_result* r);
+void or_nq_search_from(int N, int g, const or_nq_node* nodes, int n, uint64_t* tree, uint64_t* sol);
+int or_nq_frontier(int N, int g, int depth, or_nq_node* out, int cap, uint64_t* tree, uint64_t* sol);
 /* nqueens_gpu_chpl.chpl:152-248 / nqueens_multigpu_chpl.chpl:158-352 with the oracle as evaluator;
  * D >= 1 emulates the static strided split (no work stealing) sequentially. */
 void or_nq_search_offload(int N, int g, int m, int M, int D, or_search_result* r);
