@@ -213,10 +213,21 @@ def dist_init(backend):
     return world
 
 
-def dist_barrier(world):
+_CPU_GROUP = None
+
+
+def dist_barrier(world, cpu=False):
+    """cpu=True: wait on the host (a gloo group).  An NCCL barrier is a kernel that spins on every waiting rank's
+    GPU — while rank 0 drives all GPUs through a multi-GPU search that would take SMs away from the search."""
+    global _CPU_GROUP
     if world > 1:
         import torch.distributed as dist
-        dist.barrier()
+        if cpu and dist.get_backend() != "gloo":
+            if _CPU_GROUP is None:
+                _CPU_GROUP = dist.new_group(backend="gloo")
+            dist.barrier(group=_CPU_GROUP)
+        else:
+            dist.barrier()
 
 
 def dist_max_sum(world, t_seconds, units, device):
@@ -351,6 +362,8 @@ def run_headline_multi(steps, warmup, world, rank, M=M_HEAD, N=N_HEAD):
     dev = torch.device(f"cuda:{rank}")
     out = None
     dist_barrier(world)
+    torch.cuda.synchronize(dev)
+    dist_barrier(world, cpu=True)  # from here on the waiting ranks leave their GPUs alone
     if rank == 0:
         want = GOLDEN_NQ[N]
         for _ in range(warmup):
@@ -373,8 +386,7 @@ def run_headline_multi(steps, warmup, world, rank, M=M_HEAD, N=N_HEAD):
                "launches_per_step": launches // steps, "rounds": int(st.offloads) * steps, "offloads": int(st.offloads),
                "steps": steps, "h2d": 21 * m_HEAD * world, "d2h": (64 + 21 * m_HEAD) * world, "steals": steals / steps,
                "per_gpu_share": shares, "create_ms": None}
-    dist_barrier(world)
-    torch.cuda.synchronize(dev)
+    dist_barrier(world, cpu=True)
     return out
 
 
@@ -659,6 +671,8 @@ def main():
             for name, r in (("nq_evaluate_kernel<17>", big), ("pfsp_lb1_kernel<ta014>", pf), ("pfsp_lb2_kernel<ta020>", l2)):
                 kernels[name] = {k: r["roofline"][k] for k in ("kernel_us", "achieved", "frac", "traffic", "bytes_per_launch")}
     # ------------------------------------------------------------------ secondary: other whole searches
+    torch.cuda.synchronize()
+    dist_barrier(world, cpu=True)
     if not args.no_search and rank == 0:
         srch = {"note": "explored tree / wall time of whole searches on pre-created handles (tsb_*_search_on: step 1 and "
                         "3 on the CPU, pool of step 2 resident in HBM); set-up (handle, tables, first arena) in setup_ms"}
@@ -679,7 +693,7 @@ def main():
                 srch["nqueens_N19_D8_M50000"] = search_multi(19, 50000, 8)
                 srch["nqueens_N19_D8_bigM"] = search_multi(19, 1 << 24, 8)
         line["search"] = srch
-    dist_barrier(world)
+    dist_barrier(world, cpu=True)
     if rank == 0:
         line["kernels"] = kernels
         if world == 1 and not args.no_cpu:
@@ -687,7 +701,7 @@ def main():
         emit(line)
     if world > 1:
         import torch.distributed as dist
-        dist.barrier()
+        dist_barrier(world, cpu=True)
         dist.destroy_process_group()
 
 
