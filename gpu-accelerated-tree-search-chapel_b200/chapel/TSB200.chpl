@@ -27,6 +27,8 @@ module TSB200 {
   extern proc tsb_strerror(code: c_int): c_ptrConst(c_char);
   extern proc tsb_last_cuda_error(): c_ptrConst(c_char);
   extern proc tsb_device_count(): c_int;
+  extern proc tsb_init_devices(n: c_int): c_int;
+  extern proc tsb_bind_thread_to_device(device: c_int): c_int;  // first statement of every per-GPU task
 
   extern proc tsb_nq_create(ref h: c_ptr(tsb_nq), device: c_int, N: c_int, g: c_int, M_max: c_int): c_int;
   extern proc tsb_nq_destroy(h: c_ptr(tsb_nq)): void;

@@ -1,7 +1,10 @@
 // tsb200_api.cu — C ABI of libtsb200.so (include/tsb200.h): handles, transfers, kernel launches.
 #include <cuda_runtime.h>
 
+#include <sched.h>
+
 #include <algorithm>
+#include <cctype>
 #include <atomic>
 #include <chrono>
 #include <climits>
@@ -15,6 +18,7 @@
 
 #include "nq_expand.cuh"
 #include "nq_rounds.cuh"
+#include "nq_rounds_ll.cuh"
 #include "pfsp_expand.cuh"
 #include "nq_kernel.cuh"
 #include "pfsp_kernels.cuh"
@@ -466,6 +470,25 @@ struct RoundsCtx {
   int ctas = 0;       // grid size (env TSB200_ROUNDS_CTAS; 0 = two CTAs per three SMs: an all-to-all flag exchange
                       // among 148 CTAs costs 2-3x one among 74 (tools/flag_exchange.py), the per-CTA work grows
                       // the other way; measured best around 100 CTAs of 256 threads)
+  int version = 3;    // 3 = the fence-free kernel on the fat arena (nq_rounds_ll.cuh); 2 = nq_rounds.cuh (env TSB200_ROUNDS_V)
+  tsb::FatNode* d_fat = nullptr;  // the pool in the self-validating 64-byte format, while the LL kernel owns it
+  long long fat_cap = 0;
+  bool in_fat = false;            // the pool currently lives in d_fat (the plain arena is stale)
+  bool attr_ll = false;
+  tsb::LlSync* d_ll = nullptr;
+  int ensure_fat(long long cap, cudaStream_t s) {
+    if (!d_ll) {
+      TSB_CUDA(cudaMalloc(&d_ll, sizeof(tsb::LlSync)));
+      TSB_CUDA(cudaMemsetAsync(d_ll, 0, sizeof(tsb::LlSync), s));
+    }
+    if (cap <= fat_cap) return TSB_OK;
+    if (d_fat) cudaFree(d_fat);
+    d_fat = nullptr;
+    fat_cap = 0;
+    TSB_CUDA(cudaMalloc(&d_fat, static_cast<size_t>(cap) * sizeof(tsb::FatNode)));
+    fat_cap = cap;
+    return TSB_OK;
+  }
   unsigned long long* d_aux = nullptr;  // side word per arena position (nq_rounds.cuh)
   long long aux_cap = 0, aux_valid = 0;
   int ensure_aux(long long cap) {
@@ -483,6 +506,7 @@ struct RoundsCtx {
       if (x == 256 || x == 512) threads = x;
     }
     if (const char* v = std::getenv("TSB200_ROUNDS_CTAS")) ctas = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("TSB200_ROUNDS_V")) version = std::atoi(v) == 2 ? 2 : 3;
     if (!d_sync) {
       TSB_CUDA(cudaMalloc(&d_sync, sizeof(tsb::RoundsSync)));
       TSB_CUDA(cudaMemsetAsync(d_sync, 0, sizeof(tsb::RoundsSync), s));
@@ -497,10 +521,15 @@ struct RoundsCtx {
     if (d_sync) cudaFree(d_sync);
     if (h_state) cudaFreeHost(h_state);
     if (d_aux) cudaFree(d_aux);
+    if (d_fat) cudaFree(d_fat);
+    if (d_ll) cudaFree(d_ll);
     d_sync = nullptr;
     h_state = d_state = nullptr;
     d_aux = nullptr;
-    aux_cap = aux_valid = 0;
+    d_fat = nullptr;
+    d_ll = nullptr;
+    aux_cap = aux_valid = fat_cap = 0;
+    in_fat = false;
   }
 };
 
@@ -519,6 +548,8 @@ struct tsb_nq : Base {
 };
 
 namespace {
+
+int nq_materialize(tsb_nq* h);  // (defined with the LL kernel's launch helpers below)
 
 template <int N, int VAR, int T>
 int launch_nq_nt(tsb_nq* h, int slot, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
@@ -1020,6 +1051,51 @@ int tsb_device_count(void) {
   return n;
 }
 
+// NUMA placement of a host thread that feeds one GPU (SCALE_r01: eight zero-copy streams through one socket's
+// memory controllers and the inter-socket link cost half of the 8-GPU e2e throughput): pin the CALLING thread to
+// the cores local to `device` (sysfs local_cpulist of its PCI function); pages the thread touches first afterwards
+// — its chunk arrays, the library's pinned staging buffers — then live on that GPU's NUMA node.
+int tsb_bind_thread_to_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    (void)cudaGetLastError();
+    return TSB_ENODEV;
+  }
+  char bus[64] = {0};
+  TSB_CUDA(cudaDeviceGetPCIBusId(bus, sizeof(bus) - 1, device));
+  for (char* c = bus; *c; ++c) *c = static_cast<char>(std::tolower(static_cast<unsigned char>(*c)));
+  const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+  std::FILE* f = std::fopen(path.c_str(), "r");
+  if (!f) return TSB_EUNSUPPORTED;
+  char line[4096] = {0};
+  const bool got = std::fgets(line, sizeof(line) - 1, f) != nullptr;
+  std::fclose(f);
+  if (!got) return TSB_EUNSUPPORTED;
+  cpu_set_t want, have;
+  CPU_ZERO(&want);
+  int count = 0;
+  for (const char* p = line; *p;) {  // "0-31,64-95"
+    char* end = nullptr;
+    const long a = std::strtol(p, &end, 10);
+    if (end == p) break;
+    long b = a;
+    p = end;
+    if (*p == '-') {
+      b = std::strtol(p + 1, &end, 10);
+      p = end;
+    }
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET(static_cast<int>(c), &want);
+    if (*p == ',') ++p;
+  }
+  if (sched_getaffinity(0, sizeof(have), &have) != 0) return TSB_EUNSUPPORTED;
+  cpu_set_t both;
+  CPU_AND(&both, &want, &have);  // never outside what the process was given (containers, taskset)
+  count = CPU_COUNT(&both);
+  if (count == 0) return TSB_EUNSUPPORTED;
+  if (sched_setaffinity(0, sizeof(both), &both) != 0) return TSB_EUNSUPPORTED;
+  return count;
+}
+
 int tsb_init_devices(int n) {
   int have = 0;
   if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1) {
@@ -1142,8 +1218,10 @@ int tsb_nq_pool_push(tsb_nq* h, const void* nodes, int64_t n) {
   if (!h || n < 0 || (n && !nodes)) return TSB_EINVAL;
   TSB_CUDA(cudaSetDevice(h->device));
   nq_pool_setup(h);
+  int rc = nq_materialize(h);
+  if (rc != TSB_OK) return rc;
   h->rounds.aux_valid = 0;  // (the side words of the persistent kernel describe the pool it left behind)
-  int rc = h->pool.reserve(h->stream, n, nq_pool_min_cap(h));
+  rc = h->pool.reserve(h->stream, n, nq_pool_min_cap(h));
   if (rc != TSB_OK) return rc;
   if (n == 0) return TSB_OK;
   const long long at = h->pool.top();
@@ -1168,13 +1246,14 @@ int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_ch
   DevicePool& p = h->pool;
   if (p.size < m) return TSB_OK;  // popBackBulk returns 0 below m (lib/commons/Pool.chpl:50-59)
   TSB_CUDA(cudaSetDevice(h->device));
+  int rc = nq_materialize(h);
+  if (rc != TSB_OK) return rc;
   h->rounds.aux_valid = 0;
   const long long n = std::min<long long>(p.size, M);
   // room above the top for the worst case (every slot of every parent survives); the chunk itself is read
   // in place, as the newest pieces of the extent stack
   std::vector<PoolExtent> pieces;
   pool_top_pieces(p, n, &pieces);
-  int rc = TSB_OK;
   if (pieces.size() > tsb::EXP_MAX_PIECES)
     rc = p.compact(h->stream, p.cap);
   if (rc == TSB_OK) rc = p.reserve(h->stream, n * h->N, nq_pool_min_cap(h));
@@ -1230,6 +1309,70 @@ int nq_rounds_launch(tsb_nq* h, const tsb::RoundsParams& prm, int grid, cudaStre
   }
   return TSB_EINVAL;
 }
+template <int N>
+int nq_ll_launch_n(tsb_nq* h, const tsb::LlParams& prm, int grid, cudaStream_t s) {
+  auto kernel = tsb::nq_rounds_ll_kernel<N, tsb::LL_T>;
+  const size_t smem = sizeof(tsb::LlSmem<tsb::LL_T>) + 128;
+  if (!h->rounds.attr_ll) {
+    TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    h->rounds.attr_ll = true;
+  }
+  void* args[] = {const_cast<tsb::LlParams*>(&prm)};
+  TSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid), dim3(tsb::LL_T + 32), args, smem, s));
+  h->launches++;
+  return TSB_OK;
+}
+template <int N>
+int nq_ll_import_n(tsb_nq* h, long long size, cudaStream_t s) {
+  if (size > 0) {
+    tsb::nq_fat_import_kernel<N><<<static_cast<unsigned>((size + 255) / 256), 256, 0, s>>>(
+        h->pool.arena[h->pool.cur], h->rounds.d_fat, size, h->rounds.epoch);
+    TSB_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+  return TSB_OK;
+}
+int nq_ll_launch(tsb_nq* h, const tsb::LlParams& prm, int grid, cudaStream_t s) {
+  switch (h->N) {
+#define TSB_NQ_CASE(n) \
+  case n:              \
+    return nq_ll_launch_n<n>(h, prm, grid, s);
+    TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
+    TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
+    TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
+    TSB_NQ_CASE(20)
+#undef TSB_NQ_CASE
+  }
+  return TSB_EINVAL;
+}
+int nq_ll_import(tsb_nq* h, long long size, cudaStream_t s) {
+  switch (h->N) {
+#define TSB_NQ_CASE(n) \
+  case n:              \
+    return nq_ll_import_n<n>(h, size, s);
+    TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
+    TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
+    TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
+    TSB_NQ_CASE(20)
+#undef TSB_NQ_CASE
+  }
+  return TSB_EINVAL;
+}
+// the pool back in the plain 21-byte arena (whoever needs the node records calls this first)
+int nq_materialize(tsb_nq* h) {
+  if (!h->rounds.in_fat) return TSB_OK;
+  TSB_CUDA(cudaSetDevice(h->device));
+  const long long size = h->pool.size;
+  if (size > 0) {
+    tsb::nq_fat_export_kernel<<<static_cast<unsigned>((size + 255) / 256), 256, 0, h->stream>>>(
+        h->rounds.d_fat, h->pool.arena[h->pool.cur], size);
+    TSB_CUDA(cudaGetLastError());
+    h->launches++;
+    TSB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  h->rounds.in_fat = false;
+  return TSB_OK;
+}
 bool env_no_rounds() {
   const char* v = std::getenv("TSB200_NO_ROUNDS");
   return v && *v && *v != '0';
@@ -1262,6 +1405,71 @@ int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rou
       *n_parents += static_cast<uint64_t>(np);
       *n_children += nc;
       *n_solutions += ns;
+    }
+    return TSB_OK;
+  }
+  nq_pool_setup(h);
+  if (h->rounds.version == 3 && static_cast<long long>(M) <= static_cast<long long>(grid) * tsb::LL_SLICE) {
+    // ---- the fence-free kernel on the fat arena (nq_rounds_ll.cuh)
+    while (p.size >= m && static_cast<int64_t>(*n_rounds) < max_rounds) {
+      const long long n = std::min<long long>(p.size, M);
+      const long long need = p.size - n + n * h->N;
+      if (!h->rounds.in_fat) {
+        // the plain pool as ONE contiguous stack [0, size) with room for the worst case of the next round
+        if (need > p.cap)
+          rc = p.compact(h->stream, std::max<long long>(2 * p.cap, need + need / 2));
+        else if (p.ext.size() != 1 || p.ext[0].b != 0)
+          rc = p.compact(h->stream, p.cap);
+        if (rc == TSB_OK) rc = h->rounds.ensure_fat(p.cap, h->stream);
+        if (rc == TSB_OK) rc = nq_ll_import(h, p.size, h->stream);
+        if (rc != TSB_OK) return rc;
+        h->rounds.in_fat = true;
+      } else if (need > p.cap) {
+        rc = nq_materialize(h);
+        if (rc != TSB_OK) return rc;
+        continue;  // (grows and imports again)
+      }
+      tsb::LlParams prm;
+      prm.fat = h->rounds.d_fat;
+      prm.cap = std::min(p.cap, h->rounds.fat_cap);
+      prm.size0 = p.size;
+      prm.epoch0 = h->rounds.epoch;
+      prm.m = m;
+      prm.M = M;
+      prm.max_rounds = max_rounds - static_cast<int64_t>(*n_rounds);
+      prm.prof = std::getenv("TSB200_ROUNDS_PROF") != nullptr;
+      prm.sync = h->rounds.d_ll;
+      prm.state = h->rounds.d_state;
+      h->rounds.h_state->exit_code = -1;
+      rc = nq_ll_launch(h, prm, grid, h->stream);
+      if (rc != TSB_OK) return rc;
+      TSB_CUDA(cudaStreamSynchronize(h->stream));
+      const tsb::RoundsState st = *h->rounds.h_state;
+      if (st.exit_code < 0 || st.exit_code == tsb::RND_EXIT_ABORT) {
+        g_last_cuda_error = "nq_rounds_ll_kernel: watchdog abort (a flag exchange or a node poll did not complete)";
+        return TSB_ECUDA;
+      }
+      if (prm.prof)
+        std::fprintf(stderr, "[tsb200] LL rounds kernel: %llu rounds; CTA 0 cycles per round: fence-check %.0f poll-nodes %.0f "
+                     "scan+items %.0f build+gather %.0f store %.0f signal %.0f\n", static_cast<unsigned long long>(st.rounds),
+                     1.0 * st.prof[0] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[1] / std::max<unsigned long long>(1, st.rounds),
+                     1.0 * st.prof[2] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[3] / std::max<unsigned long long>(1, st.rounds),
+                     1.0 * st.prof[4] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[5] / std::max<unsigned long long>(1, st.rounds));
+      h->rounds.epoch = st.epoch;
+      p.size = st.size;
+      p.ext.clear();
+      if (p.size) p.ext.push_back({0, p.size});
+      *n_rounds += st.rounds;
+      *n_parents += st.parents;
+      *n_children += st.children;
+      *n_solutions += st.solutions;
+      if (st.exit_code == tsb::RND_EXIT_SPACE) {
+        if (st.rounds == 0 && need <= p.cap) return TSB_ENOMEM;  // (cannot happen)
+        rc = nq_materialize(h);  // back to the plain arena, which then grows
+        if (rc != TSB_OK) return rc;
+        continue;
+      }
+      break;  // DONE or PAUSE
     }
     return TSB_OK;
   }
@@ -1327,9 +1535,16 @@ int tsb_nq_pool_steal(tsb_nq* victim, tsb_nq* thief, int m, int64_t* n_stolen) {
   nq_pool_setup(victim);
   nq_pool_setup(thief);
   long long n = 0;
+  if (victim->pool.size < 2LL * m) {
+    *n_stolen = 0;
+    return TSB_OK;
+  }
+  int rc = nq_materialize(victim);
+  if (rc == TSB_OK) rc = nq_materialize(thief);
+  if (rc != TSB_OK) return rc;
   victim->rounds.aux_valid = 0;
   thief->rounds.aux_valid = 0;
-  int rc = pool_steal_front(victim->pool, victim->device, victim->stream, thief->pool, thief->device, thief->stream, m,
+  rc = pool_steal_front(victim->pool, victim->device, victim->stream, thief->pool, thief->device, thief->stream, m,
                             nq_pool_min_cap(thief), &n);
   *n_stolen = n;
   return rc;
@@ -1378,6 +1593,7 @@ int tsb_nq_pool_drain(tsb_nq* h, void* nodes, int64_t capacity, int64_t* n) {
   *n = p.size;
   if (p.size > capacity) return TSB_ENOMEM;
   TSB_CUDA(cudaSetDevice(h->device));
+  if (int rc = nq_materialize(h); rc != TSB_OK) return rc;
   long long at = 0;
   for (const PoolExtent& x : p.ext) {  // extents are the pool in logical (oldest first) order
     int rc = h->copy_d2h(static_cast<uint8_t*>(nodes) + at * sizeof(tsb_nq_node),

@@ -142,6 +142,10 @@ struct GpuTaskResult {
 };
 
 // one GPU task's offload loop (nqueens_gpu_chpl.chpl:197-215; nqueens_multigpu_chpl.chpl:234-253)
+inline void bind_task(int device, bool multi) {  // one host thread per GPU: next to its GPU (env TSB200_NO_NUMA=1: no)
+  if (multi && !std::getenv("TSB200_NO_NUMA")) (void)tsb_bind_thread_to_device(device);
+}
+
 void nq_gpu_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResult& r) {
   tsb_nq* h = nullptr;
   r.rc = tsb_nq_create(&h, device, N, g, M);
@@ -679,7 +683,10 @@ int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out) {
     static_split(pool, D, multi);
     std::vector<std::thread> th;
     for (int gid = 0; gid < D; gid++)
-      th.emplace_back([&, gid] { nq_gpu_task(gid % ndev, N, g, m, M, multi[gid], res[gid]); });
+      th.emplace_back([&, gid] {
+        bind_task(gid % ndev, true);
+        nq_gpu_task(gid % ndev, N, g, m, M, multi[gid], res[gid]);
+      });
     for (auto& x : th) x.join();
     for (int gid = 0; gid < D; gid++)  // leftovers back to the global pool (:315-320)
       while (multi[gid].popBack(parent)) pool.pushBack(parent);
@@ -751,7 +758,10 @@ static int nq_search_device_impl(int N, int g, int m, int M, int D, int part, in
     StealBoard* sb = std::getenv("TSB200_NO_STEAL") ? nullptr : &board;
     std::vector<std::thread> th;
     for (int gid = 0; gid < D; gid++)
-      th.emplace_back([&, gid] { nq_devpool_task(gid % ndev, N, g, m, M, multi[gid], res[gid], sb, gid); });
+      th.emplace_back([&, gid] {
+        bind_task(gid % ndev, true);
+        nq_devpool_task(gid % ndev, N, g, m, M, multi[gid], res[gid], sb, gid);
+      });
     for (auto& x : th) x.join();
     for (int gid = 0; gid < D; gid++)
       while (multi[gid].popBack(parent)) pool.pushBack(parent);
@@ -829,7 +839,10 @@ static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, 
     StealBoard* sb = (devpool && ub == 1 && !std::getenv("TSB200_NO_STEAL")) ? &board : nullptr;
     std::vector<std::thread> th;
     for (int gid = 0; gid < D; gid++)
-      th.emplace_back([&, gid] { task(gid % ndev, t, lb_kind, m, M, multi[gid], res[gid], sb, gid); });
+      th.emplace_back([&, gid] {
+        bind_task(gid % ndev, true);
+        task(gid % ndev, t, lb_kind, m, M, multi[gid], res[gid], sb, gid);
+      });
     for (auto& x : th) x.join();
     for (int gid = 0; gid < D; gid++)
       while (multi[gid].popBack(parent)) pool.pushBack(parent);

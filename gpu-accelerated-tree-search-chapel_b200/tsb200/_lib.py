@@ -56,6 +56,7 @@ SYMBOLS = {
     "tsb_last_cuda_error": (C.c_char_p, []),
     "tsb_device_count": (_i, []),
     "tsb_init_devices": (_i, [_i]),
+    "tsb_bind_thread_to_device": (_i, [_i]),
     "tsb_version": (C.c_char_p, []),
     "tsb_nq_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
     "tsb_nq_destroy": (None, [_vp]),

@@ -81,6 +81,11 @@ int tsb_device_count(void);            /* >= 0, or TSB_ENODEV */
 /* create the CUDA context of devices 0..n-1 now (the Chapel runtime does this at program start); the
  * emulation drivers call it before starting their timers */
 int tsb_init_devices(int n);
+/* pin the CALLING host thread to the CPU cores local to `device` (its PCI function's NUMA node), so that the
+ * arrays the thread allocates afterwards and the library's staging buffers sit next to the GPU they feed: call it
+ * at the top of every per-GPU task (Chapel: first statement inside the `coforall gpuID`, with one qthreads worker
+ * per task).  Returns the number of cores (> 0), TSB_EUNSUPPORTED where sysfs does not tell, TSB_ENODEV. */
+int tsb_bind_thread_to_device(int device);
 const char* tsb_version(void);
 
 /* ------------------------------------------------------------------ N-Queens ------------- */

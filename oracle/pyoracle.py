@@ -290,10 +290,25 @@ def nq_cpu_search(N: int, threads: int, depth: int = 3, use_ref: bool | None = N
             "reference" if use_ref else "port")
 
 
-def ref_pfsp() -> C.CDLL:
-    global _ref_pf
+_ref_pf_chapel = None
+
+
+def ref_pfsp(chapel_heads: bool = False) -> C.CDLL:
+    """the reference's PFSP C sources as a library; chapel_heads=True: the build in which the one line of
+    fill_min_heads_tails that differs from the Chapel program says what the Chapel line says (oracle/Makefile)"""
+    global _ref_pf, _ref_pf_chapel
+    if chapel_heads:
+        if _ref_pf_chapel is None:
+            _ref_pf_chapel = _load_ref_pfsp("libref_pfsp_chapel.so")
+        return _ref_pf_chapel
     if _ref_pf is None:
-        L = C.CDLL(os.path.join(HERE, "_ref", "libref_pfsp.so"))
+        _ref_pf = _load_ref_pfsp("libref_pfsp.so")
+    return _ref_pf
+
+
+def _load_ref_pfsp(name: str) -> C.CDLL:
+    if True:
+        L = C.CDLL(os.path.join(HERE, "_ref", name))
         L.new_bound_data.argtypes = [C.c_int, C.c_int]
         L.new_bound_data.restype = C.POINTER(RefLb1)
         L.new_johnson_bd_data.argtypes = [C.POINTER(RefLb1)]
@@ -314,13 +329,12 @@ def ref_pfsp() -> C.CDLL:
                                               C.c_int, C.c_int, C.c_void_p]
         L.ref_pfsp_evaluate_range_rep.argtypes = [C.POINTER(RefLb1), C.POINTER(RefLb2), C.c_int, C.c_void_p, C.c_int,
                                                   C.c_int, C.c_int, C.c_void_p, C.c_int]
-        _ref_pf = L
-    return _ref_pf
+    return L
 
 
-def ref_pfsp_data(inst: int):
+def ref_pfsp_data(inst: int, chapel_heads: bool = False):
     """(lb1*, lb2*) built by the reference's own functions, as pfsp_c.c:236-246 does"""
-    L = ref_pfsp()
+    L = ref_pfsp(chapel_heads)
     jobs, machines = lib().or_taillard_nb_jobs(inst), lib().or_taillard_nb_machines(inst)
     d1 = L.new_bound_data(jobs, machines)
     L.taillard_get_processing_times(d1.contents.p_times, inst)

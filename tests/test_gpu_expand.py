@@ -160,7 +160,7 @@ def test_pool_run_equals_the_same_number_of_pool_steps(N, m, M, rounds):
         assert got == tot and a.pool_size == b.pool_size
         ra, rb = a.pool_drain(), b.pool_drain()
         assert ra.tobytes() == rb.tobytes()
-        assert b.kernel_launches <= 3
+        assert b.kernel_launches <= 5  # three launches of the rounds kernel (+ the fat-arena import / export)
 
 
 def test_pool_run_against_the_oracle_rule_and_growth(monkeypatch):

@@ -281,14 +281,17 @@ def test_pfsp_golden_vectors_from_reference(golden_dir, inst):
             np.testing.assert_array_equal(got[live], gold[f"{tag}_{key}"].reshape(-1, jobs)[live], err_msg=key)
 
 
-def test_pfsp_root_uses_min_heads():
-    """limit1 == -1 is only ever evaluated by lb1_d: front = min_heads as handed to create"""
-    for inst in (14, 20):
+def test_pfsp_root_uses_min_heads(golden_dir):
+    """limit1 == -1 is only ever evaluated by lb1_d: front = min_heads as handed to create; the values
+    are those of the reference's C code built with the Chapel statement (tests/golden/pfsp_chapel_heads.json)"""
+    gold = json.load(open(os.path.join(golden_dir, "pfsp_chapel_heads.json")))
+    for inst in (1, 14, 20):
         with tsb200.PfspEvaluator(inst, M=16) as ev:
             root = np.zeros(1, dtype=tsb200.PFSP_NODE_DTYPE)
             root["limit1"] = -1
             root["prmu"][0, :] = np.arange(20)
-            check_pfsp(ev, root, "lb1_d", int(tsb200.lib().tsb_taillard_best_ub(inst)))
+            got = check_pfsp(ev, root, "lb1_d", int(tsb200.lib().tsb_taillard_best_ub(inst)))
+            assert list(got.reshape(-1)[:20]) == gold["root_lb1_children_bounds"][f"ta{inst:03d}"]
             check_pfsp(ev, root, "lb1", INT_MAX)   # lb1 / lb2 on the root: children have limit1 = 0
             check_pfsp(ev, root, "lb2", INT_MAX)
 

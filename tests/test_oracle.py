@@ -66,6 +66,27 @@ def test_chapel_min_heads_known_answers(counts):
         assert list(t.arr("min_heads", t.machines)) == counts["chapel_min_heads"][name]
 
 
+def test_chapel_min_heads_on_reference_run_output(golden_dir):
+    """the one place where the Chapel program differs from the C baseline, pinned on the output of the reference's
+    own C code built with that one line rewritten to the Chapel statement (tests/golden/make_golden_chapel.py):
+    min_heads of ta001..ta030 and the bounds of the root's children (the only node that reads min_heads)"""
+    gold = json.load(open(os.path.join(golden_dir, "pfsp_chapel_heads.json")))
+    for inst in range(1, 31):
+        tag = f"ta{inst:03d}"
+        t = po.tables(inst, heads_mode=0)
+        assert list(t.arr("min_heads", t.machines)) == gold["min_heads"][tag]
+        root = np.zeros(1, dtype=po.PFSP_NODE_DTYPE)
+        root["limit1"] = -1
+        root["prmu"][0, : t.jobs] = np.arange(t.jobs)
+        got = po.pfsp_evaluate(t, 0, root, INT_MAX).reshape(-1)[: t.jobs]  # lb1_d: bounds[k] = lb_begin[prmu[k]]
+        assert list(got) == gold["root_lb1_children_bounds"][tag]
+        if inst in (14, 20):  # ... and they do differ from the C baseline's there
+            c = po.tables(inst, heads_mode=1)
+            assert list(c.arr("min_heads", c.machines)) != gold["min_heads"][tag]
+    r = po.pfsp_search_seq(14, 0, 1, 0)
+    assert (r.tree, r.sol, r.best) == tuple(gold["counts"]["ta014_lb1d"][k] for k in ("tree", "sol", "best"))
+
+
 @pytest.mark.parametrize("inst", [1, 14, 20, 21])
 def test_bounds_match_reference(pf_gold, inst):
     tag = f"ta{inst:03d}"
