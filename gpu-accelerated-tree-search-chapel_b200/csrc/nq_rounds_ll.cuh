@@ -20,6 +20,11 @@
 // fence and publishes fence_done[cta] = epoch; a reader of old nodes first checks that every CTA has fenced the
 // round before the previous one (normally long true: one sweep of 98 flags).
 //
+// Measured alternatives for the one remaining exchange (all ~130 CTAs polling the 2 G count words: 2 500-4 000 cycles):
+// a dedicated aggregator CTA that scans the counts and writes every worker its own result line (two contention-free
+// hops: 2 900-3 400 cycles, no gain), per-reader rows that only their owner polls (no gain at 128 CTAs), CTAs of 512
+// threads (slower scan), fewer CTAs (cheaper exchange, more work per CTA: best at 128 of 148 SMs).
+//
 // The worker/fence split uses named barriers (bar.sync 1, T) for the workers; the plain 21-byte arena is converted
 // to and from the fat arena by nq_fat_import / nq_fat_export (whole pool, only when the host needs the plain form:
 // drain, steal, pool_step, arena growth).
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(T + 32, 1) nq_rounds_ll_kernel(const __grid_co
   long long layer_start = prm.size0;  // positions >= layer_start were written in the previous round (none yet)
   unsigned long long rounds = 0, tot_parents = 0, tot_children = 0, tot_solutions = 0;
   int exit_code = RND_EXIT_PAUSE;
-  long long prof[6] = {0, 0, 0, 0, 0, 0}, tp = 0;
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = 0;
   const bool prof_on = prm.prof != 0 && k == 0 && t == 0;
 #define TSB_PROF(i)                  \
   if (prof_on) {                     \
@@ -401,6 +406,7 @@ __global__ void __launch_bounds__(T + 32, 1) nq_rounds_ll_kernel(const __grid_co
       }
     };
     build_window(0, min(LL_CAP, my_children));
+    TSB_PROF(6)
     // ---- (6) all-to-all: everybody's {leaves, children}; my child offset and the round's totals
     unsigned long long before0 = 0, before1 = 0, all = 0;
     if (wid == 0) {
@@ -474,7 +480,7 @@ __global__ void __launch_bounds__(T + 32, 1) nq_rounds_ll_kernel(const __grid_co
     st->solutions = tot_solutions;
     st->exit_code = exit_code;
     if (prm.prof)
-      for (int i = 0; i < 6; i++) st->prof[i] = prof[i];
+      for (int i = 0; i < 8; i++) st->prof[i] = prof[i];
   }
 #undef TSB_PROF
 }

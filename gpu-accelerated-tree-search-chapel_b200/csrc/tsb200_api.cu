@@ -1390,7 +1390,10 @@ int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rou
   int rc = h->rounds.ensure(h->stream);
   if (rc != TSB_OK) return rc;
   int grid = std::min(h->di.sms, static_cast<int>(tsb::RND_MAX_CTAS));
-  grid = h->rounds.ctas > 0 ? std::min(grid, h->rounds.ctas) : std::max(1, 2 * grid / 3);
+  if (h->rounds.version == 3)  // measured best at 128 of 148 SMs
+    grid = h->rounds.ctas > 0 ? std::min(grid, h->rounds.ctas) : std::max(1, (grid * 7 / 8) & ~1);
+  else
+    grid = h->rounds.ctas > 0 ? std::min(grid, h->rounds.ctas) : std::max(1, 2 * grid / 3);
   while (static_cast<long long>(grid) * h->rounds.threads * tsb::RND_PPT < M && grid < h->di.sms) ++grid;  // (M decides)
   const bool persistent = static_cast<long long>(M) <= static_cast<long long>(grid) * h->rounds.threads * tsb::RND_PPT &&
                           h->di.coop && !env_no_rounds();
@@ -1450,8 +1453,9 @@ int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rou
         return TSB_ECUDA;
       }
       if (prm.prof)
-        std::fprintf(stderr, "[tsb200] LL rounds kernel: %llu rounds; CTA 0 cycles per round: fence-check %.0f poll-nodes %.0f "
-                     "scan+items %.0f build+gather %.0f store %.0f signal %.0f\n", static_cast<unsigned long long>(st.rounds),
+        std::fprintf(stderr, "[tsb200] LL rounds kernel: %llu rounds; CTA 0 cycles per round: build %.0f | fence-check %.0f poll-nodes %.0f "
+                     "scan+items %.0f gather-wait %.0f store %.0f signal %.0f\n", static_cast<unsigned long long>(st.rounds),
+                     1.0 * st.prof[6] / std::max<unsigned long long>(1, st.rounds),
                      1.0 * st.prof[0] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[1] / std::max<unsigned long long>(1, st.rounds),
                      1.0 * st.prof[2] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[3] / std::max<unsigned long long>(1, st.rounds),
                      1.0 * st.prof[4] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[5] / std::max<unsigned long long>(1, st.rounds));
