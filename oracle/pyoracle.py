@@ -59,7 +59,7 @@ class SearchResult(C.Structure):
 
 def build(ref: bool = True) -> None:
     """compile liboracle.so (always) and oracle/_ref (only where /root/reference exists)"""
-    subprocess.run(["make", "-s", "-C", HERE, "liboracle.so"], check=True)
+    subprocess.run(["make", "-s", "-C", HERE, "liboracle.so", "liboracle50.so"], check=True)
     if ref and os.path.isdir("/root/reference/baselines"):
         subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
 
@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         L.or_taillard_best_ub.restype = C.c_int64
         L.or_taillard_processing_times.argtypes = [vp, i32]
         L.or_pfsp_tables_build.argtypes = [C.POINTER(Tables), i32, i32]
+        L.or_pfsp_tables_build_variant.argtypes = [C.POINTER(Tables), i32, i32, i32]
         L.or_eval_solution.argtypes = [C.POINTER(Tables), vp]
         L.or_eval_solution.restype = C.c_int32
         L.or_lb1_bound.argtypes = [C.POINTER(Tables), vp, C.c_int32, C.c_int32]
@@ -109,9 +110,12 @@ def lib() -> C.CDLL:
 
 # ---------------------------------------------------------------- convenience wrappers
 
-def tables(inst: int, heads_mode: int = 0) -> Tables:
+LB2_VARIANTS = {"full": 0, "nabeshima": 1, "lageweg": 2, "learn": 3}  # lib/pfsp/Bound_johnson.chpl:6
+
+
+def tables(inst: int, heads_mode: int = 0, variant: int = 0) -> Tables:
     t = Tables()
-    rc = lib().or_pfsp_tables_build(C.byref(t), inst, heads_mode)
+    rc = lib().or_pfsp_tables_build_variant(C.byref(t), inst, heads_mode, variant)
     if rc != 0:
         raise ValueError(f"or_pfsp_tables_build({inst}) -> {rc}")
     return t
@@ -332,9 +336,20 @@ def _load_ref_pfsp(name: str) -> C.CDLL:
     return L
 
 
-def ref_pfsp_data(inst: int, chapel_heads: bool = False):
+_ref_named = {}
+
+
+def ref_pfsp_named(name: str) -> C.CDLL:
+    """another build of the reference's PFSP sources (oracle/Makefile): "nabeshima" / "lageweg" (lb2 variants),
+    "50" (MAX_JOBS = 50)"""
+    if name not in _ref_named:
+        _ref_named[name] = _load_ref_pfsp(f"libref_pfsp{name if name == '50' else '_' + name}.so")
+    return _ref_named[name]
+
+
+def ref_pfsp_data(inst: int, chapel_heads: bool = False, L=None):
     """(lb1*, lb2*) built by the reference's own functions, as pfsp_c.c:236-246 does"""
-    L = ref_pfsp(chapel_heads)
+    L = L or ref_pfsp(chapel_heads)
     jobs, machines = lib().or_taillard_nb_jobs(inst), lib().or_taillard_nb_machines(inst)
     d1 = L.new_bound_data(jobs, machines)
     L.taillard_get_processing_times(d1.contents.p_times, inst)

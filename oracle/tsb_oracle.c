@@ -116,16 +116,30 @@ static void fill_min_heads_tails(or_pfsp_tables* t, int heads_mode) {
 
 /* lib/pfsp/Bound_johnson.chpl:50-87 (the LB2_LEARN branch is the one taken: all
  * i<j pairs in lexicographic order, identity machine_pair_order) */
-static void fill_machine_pairs(or_pfsp_tables* t) {
+static void fill_machine_pairs(or_pfsp_tables* t, int variant) {
   int c = 0;
-  for (int i = 0; i < t->machines - 1; i++)
-    for (int j = i + 1; j < t->machines; j++) {
+  if (variant == 1) { /* LB2_NABESHIMA, :72-79: (i, i+1) */
+    for (int i = 0; i < t->machines - 1; i++, c++) {
       t->mp0[c] = i;
-      t->mp1[c] = j;
+      t->mp1[c] = i + 1;
       t->mp_order[c] = c;
-      c++;
     }
-  t->pairs = c; /* = machines*(machines-1)/2, Bound_johnson.chpl:37 */
+  } else if (variant == 2) { /* LB2_LAGEWEG, :80-87: (i, last) */
+    for (int i = 0; i < t->machines - 1; i++, c++) {
+      t->mp0[c] = i;
+      t->mp1[c] = t->machines - 1;
+      t->mp_order[c] = c;
+    }
+  } else { /* LB2_FULL / LB2_LEARN */
+    for (int i = 0; i < t->machines - 1; i++)
+      for (int j = i + 1; j < t->machines; j++) {
+        t->mp0[c] = i;
+        t->mp1[c] = j;
+        t->mp_order[c] = c;
+        c++;
+      }
+  }
+  t->pairs = c; /* = machines*(machines-1)/2 resp. machines-1, Bound_johnson.chpl:36-43 */
 }
 
 /* lib/pfsp/Bound_johnson.chpl:89-104 — sum of p on the machines strictly between m1 and m2 */
@@ -182,18 +196,21 @@ static void fill_johnson_schedules(or_pfsp_tables* t) {
 }
 
 /* pfsp_chpl.chpl:31-38 (module-scope table construction) */
-int or_pfsp_tables_build(or_pfsp_tables* t, int inst, int heads_mode) {
+int or_pfsp_tables_build_variant(or_pfsp_tables* t, int inst, int heads_mode, int variant) {
   if (inst < 1 || inst > 120) return -1;
   memset(t, 0, sizeof(*t));
   t->jobs = or_taillard_nb_jobs(inst);
   t->machines = or_taillard_nb_machines(inst);
-  if (t->jobs > OR_MAX_JOBS) return -2; /* MAX_JOBS = 20: only ta001..ta030 */
+  if (t->jobs > OR_MAX_JOBS) return -2; /* MAX_JOBS (20: only ta001..ta030; 50: up to ta060) */
   or_taillard_processing_times(t->p_times, inst);
   fill_min_heads_tails(t, heads_mode);
-  fill_machine_pairs(t);
+  fill_machine_pairs(t, variant);
   fill_lags(t);
   fill_johnson_schedules(t);
   return 0;
+}
+int or_pfsp_tables_build(or_pfsp_tables* t, int inst, int heads_mode) {
+  return or_pfsp_tables_build_variant(t, inst, heads_mode, 0);
 }
 
 /* ======================================================================== lb1 family */

@@ -25,7 +25,10 @@ extern "C" {
 #endif
 
 #define OR_MAX_QUEENS 20   /* lib/nqueens/NQueens_node.chpl:7 */
-#define OR_MAX_JOBS 20     /* lib/pfsp/PFSP_node.chpl:7 */
+#ifndef OR_MAX_JOBS
+#define OR_MAX_JOBS 20     /* lib/pfsp/PFSP_node.chpl:7 (`config param MAX_JOBS`: oracle/Makefile builds a second \
+                              library with -DOR_MAX_JOBS=50 = `chpl -sMAX_JOBS=50`, for ta031..ta060) */
+#endif
 #define OR_MAX_MACHINES 20 /* lib/pfsp/Bound_simple.chpl:3 (NUM_MACHINES) */
 
 /* lib/nqueens/NQueens_node.chpl:9-11 — 21 bytes, align 1 */
@@ -34,7 +37,7 @@ typedef struct {
   uint8_t board[OR_MAX_QUEENS];
 } or_nq_node;
 
-/* lib/pfsp/PFSP_node.chpl:9-12 — 88 bytes, align 4 */
+/* lib/pfsp/PFSP_node.chpl:9-12 — 88 bytes (208 with MAX_JOBS = 50), align 4 */
 typedef struct {
   int32_t depth;
   int32_t limit1;
@@ -60,6 +63,10 @@ void or_taillard_processing_times(int32_t* ptm, int id);
 
 /* ---- table precompute; heads_mode 0 = Chapel semantics (authoritative), 1 = C-baseline semantics ---- */
 int or_pfsp_tables_build(or_pfsp_tables* t, int inst, int heads_mode);
+/* the same with one of the reference's lb2 variants (Bound_johnson.chpl:6, :36-43, :50-87): 0 LB2_FULL / 3 LB2_LEARN
+ * (all pairs, what the reference compiles), 1 LB2_NABESHIMA (adjacent machines), 2 LB2_LAGEWEG (each machine with
+ * the last one) */
+int or_pfsp_tables_build_variant(or_pfsp_tables* t, int inst, int heads_mode, int variant);
 
 /* ---- bounds ---- */
 int32_t or_eval_solution(const or_pfsp_tables* t, const int32_t* prmu);

@@ -200,3 +200,57 @@ def test_pfsp_expand_chunk_reproduces_the_offload_search(lb):
     rest, tree2, sol2, offloads, parents = _pool_search(expand, first, m, M)
     assert (offloads, parents) == (ref.offloads, ref.offloaded_parents)
     assert state["best"] == ref.best == 1377
+
+
+# ------------------------------------------------------------------------------------------ SURVEY §8(f4)
+def _oracle_tables_from_gold(gold, tag, Tables):
+    """oracle tables whose Johnson order is the reference's own (the table is an input of the bounds)"""
+    jobs, machines, pairs = (int(x) for x in gold[f"{tag}_dims"])
+    t = Tables()
+    t.jobs, t.machines, t.pairs = jobs, machines, pairs
+    for name, key, n in (("p_times", "p_times", jobs * machines), ("min_tails", "min_tails", machines),
+                         ("lags", "lags", pairs * jobs), ("johnson", "johnson_qsort", pairs * jobs),
+                         ("mp0", "mp0", pairs), ("mp1", "mp1", pairs)):
+        np.ctypeslib.as_array(getattr(t, name))[:n] = gold[f"{tag}_{key}"]
+    np.ctypeslib.as_array(t.mp_order)[:pairs] = np.arange(pairs)
+    return t
+
+
+@pytest.mark.parametrize("variant", ["nabeshima", "lageweg"])
+@pytest.mark.parametrize("inst", [14, 21])
+def test_lb2_variants_match_reference(golden_dir, variant, inst):
+    """LB2_NABESHIMA / LB2_LAGEWEG (Bound_johnson.chpl:6,36-43,50-87): the oracle's pair tables equal the ones the
+    reference's fill_* produce when compiled with that variant, and its lb2 bounds equal the reference's"""
+    gold = np.load(os.path.join(golden_dir, "pfsp_f4.npz"))
+    tag = f"{variant}_ta{inst:03d}"
+    t = po.tables(inst, 0, po.LB2_VARIANTS[variant])
+    jobs, machines, pairs = (int(x) for x in gold[f"{tag}_dims"])
+    assert (t.jobs, t.machines, t.pairs) == (jobs, machines, pairs) and pairs == machines - 1
+    np.testing.assert_array_equal(t.arr("mp0", pairs), gold[f"{tag}_mp0"])
+    np.testing.assert_array_equal(t.arr("mp1", pairs), gold[f"{tag}_mp1"])
+    np.testing.assert_array_equal(t.arr("lags", pairs * jobs), gold[f"{tag}_lags"])
+    parents = gold[f"{tag}_parents"].view(po.PFSP_NODE_DTYPE)
+    best = int(po.lib().or_taillard_best_ub(inst))
+    for tt in (t, _oracle_tables_from_gold(gold, tag, po.Tables)):  # own Johnson order and the reference's (ties)
+        np.testing.assert_array_equal(po.pfsp_evaluate(tt, 2, parents, best), gold[f"{tag}_lb2_best"])
+        np.testing.assert_array_equal(po.pfsp_evaluate(tt, 2, parents, INT_MAX), gold[f"{tag}_lb2_inf"])
+
+
+@pytest.mark.parametrize("inst", [31, 41, 51])
+def test_max_jobs_50_oracle_matches_reference(golden_dir, inst):
+    """the oracle built with OR_MAX_JOBS = 50 (208-byte nodes) against the reference's C code built with MAX_JOBS 50"""
+    from oracle import pyoracle50 as po50
+    gold = np.load(os.path.join(golden_dir, "pfsp_f4.npz"))
+    tag = f"jobs50_ta{inst:03d}"
+    t = po50.tables(inst)
+    jobs, machines, pairs = (int(x) for x in gold[f"{tag}_dims"])
+    assert (t.jobs, t.machines, t.pairs) == (jobs, machines, pairs) and jobs == 50
+    np.testing.assert_array_equal(t.arr("p_times", jobs * machines), gold[f"{tag}_p_times"])
+    np.testing.assert_array_equal(t.arr("min_tails", machines), gold[f"{tag}_min_tails"])
+    np.testing.assert_array_equal(t.arr("lags", pairs * jobs), gold[f"{tag}_lags"])
+    parents = gold[f"{tag}_parents"].view(po50.PFSP_NODE_DTYPE)
+    best = int(po.lib().or_taillard_best_ub(inst))
+    np.testing.assert_array_equal(po50.pfsp_evaluate(t, 1, parents, best), gold[f"{tag}_lb1"])
+    np.testing.assert_array_equal(po50.pfsp_evaluate(t, 0, parents, best), gold[f"{tag}_lb1_d"])
+    np.testing.assert_array_equal(po50.pfsp_evaluate(t, 2, parents, best), gold[f"{tag}_lb2_best"])
+    np.testing.assert_array_equal(po50.pfsp_evaluate(t, 2, parents, INT_MAX), gold[f"{tag}_lb2_inf"])
