@@ -48,6 +48,13 @@ module TSB200 {
                               johnson: c_ptrConst(int(32)), lags: c_ptrConst(int(32)),
                               mp0: c_ptrConst(int(32)), mp1: c_ptrConst(int(32)),
                               mp_order: c_ptrConst(int(32))): c_int;
+  // a build with `-sMAX_JOBS=50` (208-byte nodes, ta031..ta060) passes max_jobs = MAX_JOBS here
+  extern proc tsb_pfsp_create_wide(ref h: c_ptr(tsb_pfsp), device: c_int, max_jobs: c_int, jobs: c_int, machines: c_int,
+                                   M_max: c_int, p_times: c_ptrConst(int(32)), min_heads: c_ptrConst(int(32)),
+                                   min_tails: c_ptrConst(int(32)), nb_pairs: c_int,
+                                   johnson: c_ptrConst(int(32)), lags: c_ptrConst(int(32)),
+                                   mp0: c_ptrConst(int(32)), mp1: c_ptrConst(int(32)),
+                                   mp_order: c_ptrConst(int(32))): c_int;
   extern proc tsb_pfsp_destroy(h: c_ptr(tsb_pfsp)): void;
   extern proc tsb_pfsp_evaluate(h: c_ptr(tsb_pfsp), lb_kind: c_int, parents: c_ptrConst(void), count: c_int,
                                 best: int(64), bounds: c_ptr(int(32))): c_int;

@@ -22,6 +22,7 @@
 #include "pfsp_expand.cuh"
 #include "nq_kernel.cuh"
 #include "pfsp_kernels.cuh"
+#include "pfsp_wide.cuh"
 #include "tsb200.h"
 
 namespace {
@@ -784,6 +785,10 @@ struct tsb_pfsp : Base {
   bool attr_set[3] = {false, false, false};
   int occ[3] = {0, 0, 0};
   bool simd16 = false;  // lb1 / lb1_d children two per register (values < 2^16, min_tails non-increasing)
+  bool wide = false;    // MAX_JOBS = 50 build: 208-byte nodes, the general kernels of pfsp_wide.cuh
+  tsb::PfspWideTables* d_wtab = nullptr;
+  bool wide_attr[3] = {false, false, false};
+  int wide_occ[3] = {0, 0, 0};
   // fused expand + device-resident pool
   ExpandCtx ex;
   bool ex_attr[4] = {false, false, false, false};  // count lb1_d, lb1, lb2; build
@@ -839,10 +844,38 @@ int launch_lb2_m(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count, 
   return launch_lb2_mc<M>(h, *h->lb2c, in, out, count, best, s);
 }
 
+template <int KIND, int M>
+int launch_wide_km(tsb_pfsp* h, const uint8_t* in, uint8_t* out, long long count, int best, cudaStream_t s) {
+  auto kernel = tsb::pfsp_wide_kernel<KIND, M>;
+  const size_t smem = sizeof(tsb::PfspWideSmem) + 128;
+  if (!h->wide_attr[KIND]) {
+    TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    h->wide_attr[KIND] = true;
+  }
+  int grid = 1;
+  int rc = grid_for(kernel, tsb::PW_THREADS, smem, count + tsb::PW_TILE - 1, tsb::PW_TILE, h->di.sms, &grid, &h->wide_occ[KIND]);
+  if (rc != TSB_OK) return rc;
+  kernel<<<grid, tsb::PW_THREADS, smem, s>>>(in, reinterpret_cast<int32_t*>(out), count, h->d_wtab, best);
+  TSB_CUDA(cudaGetLastError());
+  h->launches++;
+  return TSB_OK;
+}
+template <int M>
+int launch_wide_m(tsb_pfsp* h, int lb_kind, const uint8_t* in, uint8_t* out, long long count, int best, cudaStream_t s) {
+  if (lb_kind == TSB_LB1_D) return launch_wide_km<0, M>(h, in, out, count, best, s);
+  if (lb_kind == TSB_LB1) return launch_wide_km<1, M>(h, in, out, count, best, s);
+  return launch_wide_km<2, M>(h, in, out, count, best, s);
+}
+
 int launch_pfsp(tsb_pfsp* h, int lb_kind, const uint8_t* in, uint8_t* out, long long count, int64_t best64,
                 cudaStream_t s) {
   // bounds are int32 and `lb > best` can never hold for best >= INT32_MAX (Chapel's max(int) under --ub 0)
   const int best = best64 > INT_MAX ? INT_MAX : best64 < INT_MIN ? INT_MIN : static_cast<int>(best64);
+  if (h->wide) {
+    if (h->mt == 5) return launch_wide_m<5>(h, lb_kind, in, out, count, best, s);
+    if (h->mt == 10) return launch_wide_m<10>(h, lb_kind, in, out, count, best, s);
+    return launch_wide_m<20>(h, lb_kind, in, out, count, best, s);
+  }
 #define TSB_PF_DISPATCH(M)                                                                                      \
   if (lb_kind == TSB_LB1)                                                                                        \
     return h->simd16 ? launch_lb1_km<1, M, true>(h, in, out, count, s) : launch_lb1_km<1, M, false>(h, in, out, count, s); \
@@ -1774,11 +1807,93 @@ int tsb_pfsp_create(tsb_pfsp** out, int device, int jobs, int machines, int M_ma
   return TSB_OK;
 }
 
+// The reference built with MAX_JOBS = max_jobs (lib/pfsp/PFSP_node.chpl:7): 20 = tsb_pfsp_create; 50 = 208-byte nodes,
+// jobs == 50 instances (ta031..ta060), evaluated by the general kernels of pfsp_wide.cuh (evaluate / evaluate_device
+// only: the fused expand and the device pool are specialised for 20 jobs)
+int tsb_pfsp_create_wide(tsb_pfsp** out, int device, int max_jobs, int jobs, int machines, int M_max, const int32_t* p_times,
+                         const int32_t* min_heads, const int32_t* min_tails, int nb_pairs, const int32_t* johnson,
+                         const int32_t* lags, const int32_t* mp0, const int32_t* mp1, const int32_t* mp_order) {
+  if (max_jobs == TSB_MAX_JOBS)
+    return tsb_pfsp_create(out, device, jobs, machines, M_max, p_times, min_heads, min_tails, nb_pairs, johnson, lags, mp0,
+                           mp1, mp_order);
+  if (!out || !p_times || !min_heads || !min_tails || M_max < 1 || nb_pairs < 0) return TSB_EINVAL;
+  if (nb_pairs > 0 && (!johnson || !lags || !mp0 || !mp1 || !mp_order)) return TSB_EINVAL;
+  if (max_jobs != TSB_MAX_JOBS_WIDE || jobs != max_jobs || machines < 1 || machines > TSB_MAX_MACHINES ||
+      nb_pairs > TSB_MAX_PAIRS)
+    return TSB_EUNSUPPORTED;
+  tsb_pfsp* h = new (std::nothrow) tsb_pfsp();
+  if (!h) return TSB_ENOMEM;
+  h->jobs = jobs;
+  h->machines = machines;
+  h->pairs = nb_pairs;
+  h->wide = true;
+  h->mt = machines <= 5 ? 5 : machines <= 10 ? 10 : 20;
+  int rc = h->init(device, M_max, tsb::PW_REC, static_cast<size_t>(jobs) * 4);
+  std::vector<tsb::PfspWideTables> tv(1);
+  tsb::PfspWideTables& t = tv[0];
+  std::memset(&t, 0, sizeof(t));
+  t.jobs = jobs;
+  t.machines = machines;
+  t.pairs = nb_pairs;
+  bool bad = false, wide_values = false;
+  for (int k = 0; k < machines; k++) {
+    t.min_heads[k] = min_heads[k];
+    t.min_tails[k] = min_tails[k];
+    for (int j = 0; j < jobs; j++) {
+      const int32_t pv = p_times[k * jobs + j];
+      t.total[k] += pv;
+      t.pj[j * tsb::PW_PSTRIDE + k] = pv;
+    }
+  }
+  for (int l = 0; l < nb_pairs; l++) {
+    const int i = mp_order[l];
+    if (i < 0 || i >= nb_pairs) {
+      bad = true;
+      continue;
+    }
+    const int a = mp0[i], b = mp1[i];
+    if (a < 0 || a >= machines || b < 0 || b >= machines) {
+      bad = true;
+      continue;
+    }
+    wide_values |= min_tails[a] < 0 || min_tails[a] > 2047 || min_tails[b] < 0 || min_tails[b] > 2047;
+    t.pair[l] = static_cast<uint32_t>(a) | static_cast<uint32_t>(b) << 5 | static_cast<uint32_t>(min_tails[a] & 2047) << 10 |
+                static_cast<uint32_t>(min_tails[b] & 2047) << 21;
+    for (int j = 0; j < jobs; j++) {
+      const int job = johnson[i * jobs + j];
+      if (job < 0 || job >= jobs) {
+        bad = true;
+        continue;
+      }
+      const int pa = p_times[a * jobs + job], pb = p_times[b * jobs + job], lg = lags[i * jobs + job];
+      wide_values |= pa < 0 || pa > 127 || pb < 0 || pb > 127 || lg < 0 || lg > 4095;
+      t.jp[l * jobs + j] = static_cast<uint32_t>(job) | static_cast<uint32_t>(pa & 127) << 6 | static_cast<uint32_t>(pb & 127) << 13 |
+                           static_cast<uint32_t>(lg & 4095) << 20;
+    }
+  }
+  if (rc == TSB_OK && bad) rc = TSB_EINVAL;
+  if (rc == TSB_OK && wide_values) h->pairs = 0;  // values outside the Taillard range: no lb2 on this handle
+  auto upload = [&]() -> int {
+    TSB_CUDA(cudaMalloc(&h->d_wtab, sizeof(t)));
+    TSB_CUDA(cudaMemcpyAsync(h->d_wtab, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
+    TSB_CUDA(cudaStreamSynchronize(h->stream));
+    return TSB_OK;
+  };
+  if (rc == TSB_OK) rc = upload();
+  if (rc != TSB_OK) {
+    tsb_pfsp_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return TSB_OK;
+}
+
 void tsb_pfsp_destroy(tsb_pfsp* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->d_tab1) cudaFree(h->d_tab1);
+  if (h->d_wtab) cudaFree(h->d_wtab);
   delete h->lb2c;
   delete h->lb2u;
   if (h->d_tabu) cudaFree(h->d_tabu);
@@ -1837,6 +1952,7 @@ uint64_t tsb_pfsp_slow_rounds(const tsb_pfsp* h) { return h ? h->slow_rounds : 0
 
 int tsb_pfsp_expand_device(tsb_pfsp* h, int lb_kind, const void* parents_d, int count, int64_t* best,
                            void* children_d, uint64_t* n_children, uint64_t* n_solutions, void* stream) {
+  if (h && h->wide) return TSB_EUNSUPPORTED;  // (the fused expand / device pool exist for MAX_JOBS = 20 only)
   if (!h || count < 0 || lb_kind < 0 || lb_kind > 2 || !best || !n_children || !n_solutions) return TSB_EINVAL;
   if (lb_kind == TSB_LB2 && h->pairs == 0) return TSB_EINVAL;
   *n_children = *n_solutions = 0;
@@ -1856,6 +1972,7 @@ int tsb_pfsp_expand_device(tsb_pfsp* h, int lb_kind, const void* parents_d, int 
 
 int tsb_pfsp_expand(tsb_pfsp* h, int lb_kind, const void* parents, int count, int64_t* best, void* children,
                     uint64_t capacity, uint64_t* n_children, uint64_t* n_solutions) {
+  if (h && h->wide) return TSB_EUNSUPPORTED;  // (the fused expand / device pool exist for MAX_JOBS = 20 only)
   if (!h || count < 0 || count > h->M_max || lb_kind < 0 || lb_kind > 2 || !best || !n_children || !n_solutions)
     return TSB_EINVAL;
   if (lb_kind == TSB_LB2 && h->pairs == 0) return TSB_EINVAL;
@@ -1884,6 +2001,7 @@ int tsb_pfsp_expand(tsb_pfsp* h, int lb_kind, const void* parents, int count, in
 }
 
 int tsb_pfsp_pool_push(tsb_pfsp* h, const void* nodes, int64_t n) {
+  if (h && h->wide) return TSB_EUNSUPPORTED;  // (the fused expand / device pool exist for MAX_JOBS = 20 only)
   if (!h || n < 0 || (n && !nodes)) return TSB_EINVAL;
   TSB_CUDA(cudaSetDevice(h->device));
   pfsp_pool_setup(h);
@@ -1906,6 +2024,7 @@ int64_t tsb_pfsp_pool_size(const tsb_pfsp* h) { return h ? h->pool.size : -1; }
 
 int tsb_pfsp_pool_step(tsb_pfsp* h, int lb_kind, int m, int M, int64_t* best, int64_t* n_parents,
                        uint64_t* n_children, uint64_t* n_solutions) {
+  if (h && h->wide) return TSB_EUNSUPPORTED;  // (the fused expand / device pool exist for MAX_JOBS = 20 only)
   if (!h || lb_kind < 0 || lb_kind > 2 || m < 1 || M < 1 || M > h->M_max || !best || !n_parents || !n_children ||
       !n_solutions)
     return TSB_EINVAL;

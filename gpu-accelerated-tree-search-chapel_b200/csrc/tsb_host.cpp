@@ -586,12 +586,16 @@ int tsb_taillard_nb_machines(int id) {
 }
 int64_t tsb_taillard_best_ub(int id) { return (id < 1 || id > 120) ? -1 : kBestUb[id - 1]; }
 
-int tsb_pfsp_tables_build(tsb_pfsp_tables* t, int inst) {
-  if (!t || inst < 1 || inst > 120) return TSB_EINVAL;
+}  // extern "C"
+namespace {
+// lbound1 / lbound2 of a Taillard instance (pfsp_gpu_chpl.chpl:325-332) into either table struct
+template <class T, int MAXJ>
+int build_tables(T* t, int inst, int variant) {
+  if (!t || inst < 1 || inst > 120 || variant < 0 || variant > 3) return TSB_EINVAL;
   std::memset(t, 0, sizeof(*t));
   const int N = t->jobs = tsb_taillard_nb_jobs(inst);
   const int M = t->machines = tsb_taillard_nb_machines(inst);
-  if (N > TSB_MAX_JOBS) return TSB_EUNSUPPORTED;  // MAX_JOBS = 20 (lib/pfsp/PFSP_node.chpl:7)
+  if (N > MAXJ) return TSB_EUNSUPPORTED;  // MAX_JOBS (lib/pfsp/PFSP_node.chpl:7): 20, or 50 for the wide tables
   int64_t seed = kSeeds[inst - 1];
   for (int i = 0; i < M; i++)  // lib/pfsp/Taillard.chpl:86-97
     for (int j = 0; j < N; j++) t->p_times[i * N + j] = static_cast<int32_t>(unif(seed, 1, 99));
@@ -615,25 +619,34 @@ int tsb_pfsp_tables_build(tsb_pfsp_tables* t, int inst) {
       acc += t->p_times[k * N + i];
     }
   }
-  // fill_machine_pairs (Bound_johnson.chpl:50-87, the branch actually taken) + fill_lags (:89-104)
+  // fill_machine_pairs (Bound_johnson.chpl:50-87: LB2_FULL / LB2_LEARN = all pairs, the branch the reference
+  // compiles; LB2_NABESHIMA = adjacent machines, LB2_LAGEWEG = each machine with the last) + fill_lags (:89-104)
   int c = 0;
-  for (int a = 0; a < M - 1; a++)
-    for (int b = a + 1; b < M; b++, c++) {
-      t->mp0[c] = a;
-      t->mp1[c] = b;
-      t->mp_order[c] = c;
-      for (int j = 0; j < N; j++) {
-        int32_t s = 0;
-        for (int k = a + 1; k < b; k++) s += t->p_times[k * N + j];
-        t->lags[c * N + j] = s;
-      }
+  const auto add_pair = [&](int a, int b) {
+    t->mp0[c] = a;
+    t->mp1[c] = b;
+    t->mp_order[c] = c;
+    for (int j = 0; j < N; j++) {
+      int32_t s = 0;
+      for (int k = a + 1; k < b; k++) s += t->p_times[k * N + j];
+      t->lags[c * N + j] = s;
     }
+    ++c;
+  };
+  if (variant == TSB_LB2_NABESHIMA) {
+    for (int a = 0; a < M - 1; a++) add_pair(a, a + 1);
+  } else if (variant == TSB_LB2_LAGEWEG) {
+    for (int a = 0; a < M - 1; a++) add_pair(a, M - 1);
+  } else {
+    for (int a = 0; a < M - 1; a++)
+      for (int b = a + 1; b < M; b++) add_pair(a, b);
+  }
   t->pairs = c;
   // fill_johnson_schedules (:145-177): Johnson's rule per pair on (p_a + lag, p_b + lag)
   for (int k = 0; k < t->pairs; k++) {
     const int a = t->mp0[k], b = t->mp1[k];
-    int order[TSB_MAX_JOBS];
-    int32_t k1[TSB_MAX_JOBS], k2[TSB_MAX_JOBS];
+    int order[MAXJ];
+    int32_t k1[MAXJ], k2[MAXJ];
     for (int j = 0; j < N; j++) {
       order[j] = j;
       k1[j] = t->p_times[a * N + j] + t->lags[k * N + j];
@@ -647,6 +660,21 @@ int tsb_pfsp_tables_build(tsb_pfsp_tables* t, int inst) {
     for (int j = 0; j < N; j++) t->johnson[k * N + j] = order[j];
   }
   return TSB_OK;
+}
+}  // namespace
+extern "C" {
+
+int tsb_pfsp_tables_build(tsb_pfsp_tables* t, int inst) { return tsb_pfsp_tables_build_variant(t, inst, TSB_LB2_FULL); }
+int tsb_pfsp_tables_build_variant(tsb_pfsp_tables* t, int inst, int variant) {
+  return build_tables<tsb_pfsp_tables, TSB_MAX_JOBS>(t, inst, variant);
+}
+int tsb_pfsp_tables50_build(tsb_pfsp_tables50* t, int inst, int variant) {
+  return build_tables<tsb_pfsp_tables50, TSB_MAX_JOBS_WIDE>(t, inst, variant);
+}
+int tsb_pfsp_create50_from_tables(tsb_pfsp** h, int device, int M_max, const tsb_pfsp_tables50* t) {
+  if (!t) return TSB_EINVAL;
+  return tsb_pfsp_create_wide(h, device, TSB_MAX_JOBS_WIDE, t->jobs, t->machines, M_max, t->p_times, t->min_heads,
+                              t->min_tails, t->pairs, t->johnson, t->lags, t->mp0, t->mp1, t->mp_order);
 }
 
 int tsb_pfsp_create_from_tables(tsb_pfsp** h, int device, int M_max, const tsb_pfsp_tables* t) {

@@ -38,6 +38,17 @@ class PfspTables(C.Structure):
     ]
 
 
+class PfspTables50(C.Structure):
+    """tsb_pfsp_tables50 (MAX_JOBS = 50 build)"""
+    _fields_ = [
+        ("jobs", C.c_int32), ("machines", C.c_int32), ("pairs", C.c_int32),
+        ("p_times", C.c_int32 * (MAX_MACHINES * 50)),
+        ("min_heads", C.c_int32 * MAX_MACHINES), ("min_tails", C.c_int32 * MAX_MACHINES),
+        ("johnson", C.c_int32 * (MAX_PAIRS * 50)), ("lags", C.c_int32 * (MAX_PAIRS * 50)),
+        ("mp0", C.c_int32 * MAX_PAIRS), ("mp1", C.c_int32 * MAX_PAIRS), ("mp_order", C.c_int32 * MAX_PAIRS),
+    ]
+
+
 class SearchStats(C.Structure):
     """tsb_search_stats"""
     _fields_ = [
@@ -77,6 +88,9 @@ SYMBOLS = {
     "tsb_nq_set_xfer": (_i, [_vp, _i]),
     "tsb_nq_kernel_launches": (_u64, [_vp]),
     "tsb_pfsp_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _pi32, _pi32, _pi32, _i, _pi32, _pi32, _pi32, _pi32, _pi32]),
+    "tsb_pfsp_create_wide": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _pi32, _pi32, _pi32, _i, _pi32, _pi32, _pi32, _pi32, _pi32]),
+    "tsb_pfsp_tables50_build": (_i, [C.POINTER(PfspTables50), _i, _i]),
+    "tsb_pfsp_create50_from_tables": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(PfspTables50)]),
     "tsb_pfsp_destroy": (None, [_vp]),
     "tsb_pfsp_evaluate": (_i, [_vp, _i, _vp, _i, _i64, _vp]),
     "tsb_pfsp_evaluate_device": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
@@ -95,6 +109,7 @@ SYMBOLS = {
     "tsb_taillard_nb_machines": (_i, [_i]),
     "tsb_taillard_best_ub": (_i64, [_i]),
     "tsb_pfsp_tables_build": (_i, [C.POINTER(PfspTables), _i]),
+    "tsb_pfsp_tables_build_variant": (_i, [C.POINTER(PfspTables), _i, _i]),
     "tsb_pfsp_create_from_tables": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(PfspTables)]),
     "tsb_nq_warmup": (_i, [_i, _i, _vp, _i64, C.POINTER(_i64), C.POINTER(_u64), C.POINTER(_u64)]),
     "tsb_nq_stream": (_vp, [_vp]),

@@ -5,30 +5,53 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import LB1, LB1_D, LB2, PfspTables, SearchStats, check, lib
+from ._lib import LB1, LB1_D, LB2, PfspTables, PfspTables50, SearchStats, check, lib
 
 # lib/pfsp/PFSP_node.chpl:9-12
 PFSP_NODE_DTYPE = np.dtype([("depth", np.int32), ("limit1", np.int32), ("prmu", np.int32, (20,))])
 assert PFSP_NODE_DTYPE.itemsize == 88
+# a build of the reference with MAX_JOBS = 50 (ta031..ta060)
+PFSP_NODE50_DTYPE = np.dtype([("depth", np.int32), ("limit1", np.int32), ("prmu", np.int32, (50,))])
+assert PFSP_NODE50_DTYPE.itemsize == 208
 # the Chapel CLI spells the bounds as strings (pfsp_gpu_chpl.chpl:15), the C ABI as the C baseline's ints
 LB_NAMES = {"lb1_d": LB1_D, "lb1": LB1, "lb2": LB2}
 
 
-def taillard_tables(inst: int) -> PfspTables:
-    """lbound1 / lbound2 as built at pfsp_gpu_chpl.chpl:325-332 (Chapel semantics, incl. its min_heads)"""
+LB2_VARIANTS = {"full": 0, "nabeshima": 1, "lageweg": 2, "learn": 3}  # lib/pfsp/Bound_johnson.chpl:6
+
+
+def taillard_tables(inst: int, variant="full") -> PfspTables:
+    """lbound1 / lbound2 as built at pfsp_gpu_chpl.chpl:325-332 (Chapel semantics, incl. its min_heads); `variant`
+    selects the machine pairs of lb2 (the reference compiles "full")"""
     t = PfspTables()
-    check(lib().tsb_pfsp_tables_build(C.byref(t), inst), "tsb_pfsp_tables_build")
+    v = LB2_VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    check(lib().tsb_pfsp_tables_build_variant(C.byref(t), inst, v), "tsb_pfsp_tables_build_variant")
+    return t
+
+
+def taillard_tables50(inst: int, variant="full") -> PfspTables50:
+    t = PfspTables50()
+    v = LB2_VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    check(lib().tsb_pfsp_tables50_build(C.byref(t), inst, v), "tsb_pfsp_tables50_build")
     return t
 
 
 class PfspEvaluator:
-    """Owns parents_d / bounds_d / lbound1_d / lbound2_d of pfsp_gpu_chpl.chpl:359-371."""
+    """Owns parents_d / bounds_d / lbound1_d / lbound2_d of pfsp_gpu_chpl.chpl:359-371.  Instances with more than
+    20 jobs (ta031..ta060) create a MAX_JOBS = 50 handle: nodes are PFSP_NODE50_DTYPE, evaluate only."""
 
-    def __init__(self, inst: int | None = None, tables: PfspTables | None = None, M: int = 50000, device: int = 0):
-        self.tables = tables if tables is not None else taillard_tables(inst)
+    def __init__(self, inst: int | None = None, tables=None, M: int = 50000, device: int = 0):
+        if tables is None:
+            tables = taillard_tables50(inst) if lib().tsb_taillard_nb_jobs(inst) > 20 else taillard_tables(inst)
+        self.tables = tables
         self.jobs, self.machines, self.M = self.tables.jobs, self.tables.machines, M
+        self.wide = isinstance(tables, PfspTables50)
+        self.node_dtype = PFSP_NODE50_DTYPE if self.wide else PFSP_NODE_DTYPE
         self._h = C.c_void_p()
-        check(lib().tsb_pfsp_create_from_tables(C.byref(self._h), device, M, C.byref(self.tables)), "tsb_pfsp_create")
+        if self.wide:
+            check(lib().tsb_pfsp_create50_from_tables(C.byref(self._h), device, M, C.byref(self.tables)), "tsb_pfsp_create_wide")
+        else:
+            check(lib().tsb_pfsp_create_from_tables(C.byref(self._h), device, M, C.byref(self.tables)), "tsb_pfsp_create")
 
     def close(self):
         if self._h:
@@ -60,7 +83,7 @@ class PfspEvaluator:
     def evaluate_gpu(self, parents: np.ndarray, size: int, best: int, lb, bounds: np.ndarray) -> None:
         """evaluate_gpu(parents_d, size, best, lbound1_d, lbound2_d, bounds_d) of pfsp_gpu_chpl.chpl:257-270 with
         the copies of :384/:386; `size` = jobs * poolSize; lb is "lb1" | "lb1_d" | "lb2" or the int code"""
-        assert parents.dtype == PFSP_NODE_DTYPE and parents.flags.c_contiguous
+        assert parents.dtype == self.node_dtype and parents.flags.c_contiguous
         assert bounds.dtype == np.int32 and bounds.flags.c_contiguous
         kind = LB_NAMES[lb] if isinstance(lb, str) else int(lb)
         if size % self.jobs:

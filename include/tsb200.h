@@ -41,6 +41,7 @@ extern "C" {
 #define TSB_MAX_JOBS 20
 #define TSB_MAX_MACHINES 20
 #define TSB_MAX_PAIRS 190
+#define TSB_MAX_JOBS_WIDE 50 /* the reference built with `-sMAX_JOBS=50` (lib/pfsp/PFSP_node.chpl:7): ta031..ta060 */
 
 typedef struct {
   uint8_t depth;
@@ -52,6 +53,12 @@ typedef struct {
   int32_t limit1;
   int32_t prmu[TSB_MAX_JOBS];
 } tsb_pfsp_node; /* 88 bytes */
+
+typedef struct {
+  int32_t depth;
+  int32_t limit1;
+  int32_t prmu[TSB_MAX_JOBS_WIDE];
+} tsb_pfsp_node50; /* 208 bytes: PFSP Node of a MAX_JOBS = 50 build */
 
 enum {
   TSB_OK = 0,
@@ -171,6 +178,13 @@ int tsb_pfsp_create(tsb_pfsp** h, int device, int jobs, int machines, int M_max,
                     const int32_t* min_heads, const int32_t* min_tails, int nb_pairs,
                     const int32_t* johnson, const int32_t* lags, const int32_t* mp0, const int32_t* mp1,
                     const int32_t* mp_order);
+/* the reference built with MAX_JOBS = max_jobs.  max_jobs == 20: tsb_pfsp_create.  max_jobs == 50:
+ * nodes are 208-byte tsb_pfsp_node50 records, jobs must be 50 (ta031..ta060), bounds[p*50 + k]; tsb_pfsp_evaluate /
+ * tsb_pfsp_evaluate_device work on such a handle (general kernels, csrc/pfsp_wide.cuh), the fused expand / pool
+ * entry points return TSB_EUNSUPPORTED.  Table layouts as for tsb_pfsp_create with jobs = 50. */
+int tsb_pfsp_create_wide(tsb_pfsp** h, int device, int max_jobs, int jobs, int machines, int M_max, const int32_t* p_times,
+                         const int32_t* min_heads, const int32_t* min_tails, int nb_pairs, const int32_t* johnson,
+                         const int32_t* lags, const int32_t* mp0, const int32_t* mp1, const int32_t* mp_order);
 void tsb_pfsp_destroy(tsb_pfsp* h);
 
 /* Replaces pfsp_gpu_chpl.chpl:384-386
@@ -228,7 +242,24 @@ int tsb_taillard_nb_jobs(int inst);      /* lib/pfsp/Taillard.chpl:29-36 */
 int tsb_taillard_nb_machines(int inst);  /* :38-52 */
 int64_t tsb_taillard_best_ub(int inst);  /* :54-70 */
 int tsb_pfsp_tables_build(tsb_pfsp_tables* t, int inst); /* pfsp_gpu_chpl.chpl:325-332, Chapel semantics */
+/* the same with one of the reference's lb2 variants (lib/pfsp/Bound_johnson.chpl:6,36-43,50-87; the reference
+ * hard-codes LB2_FULL / LB2_LEARN = all machine pairs): the pair tables are an INPUT of tsb_pfsp_create, so the
+ * kernels evaluate whichever variant they are given */
+enum { TSB_LB2_FULL = 0, TSB_LB2_NABESHIMA = 1, TSB_LB2_LAGEWEG = 2, TSB_LB2_LEARN = 3 };
+int tsb_pfsp_tables_build_variant(tsb_pfsp_tables* t, int inst, int variant);
 int tsb_pfsp_create_from_tables(tsb_pfsp** h, int device, int M_max, const tsb_pfsp_tables* t);
+/* the same for a MAX_JOBS = 50 build (ta031..ta060) */
+typedef struct {
+  int32_t jobs, machines, pairs;
+  int32_t p_times[TSB_MAX_MACHINES * TSB_MAX_JOBS_WIDE];
+  int32_t min_heads[TSB_MAX_MACHINES];
+  int32_t min_tails[TSB_MAX_MACHINES];
+  int32_t johnson[TSB_MAX_PAIRS * TSB_MAX_JOBS_WIDE];
+  int32_t lags[TSB_MAX_PAIRS * TSB_MAX_JOBS_WIDE];
+  int32_t mp0[TSB_MAX_PAIRS], mp1[TSB_MAX_PAIRS], mp_order[TSB_MAX_PAIRS];
+} tsb_pfsp_tables50;
+int tsb_pfsp_tables50_build(tsb_pfsp_tables50* t, int inst, int variant);
+int tsb_pfsp_create50_from_tables(tsb_pfsp** h, int device, int M_max, const tsb_pfsp_tables50* t);
 
 /* ------------------------------------------------------------------ emulation of the Chapel drivers
  * (same 3-step search, same Pool contract, same --m/--M/--D meaning; used for measurement

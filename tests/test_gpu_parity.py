@@ -321,3 +321,63 @@ def test_pfsp_full_search_ta020_lb2(golden_dir):
     counts = json.load(open(os.path.join(golden_dir, "counts.json")))["pfsp"]["ta020_lb2_ub1"]
     st = tsb200.pfsp_search(20, "lb2", 1, 25, 50000, 1)
     assert (st.explored_tree, st.explored_sol, st.best) == (counts["tree"], counts["sol"], counts["best"])
+
+
+@pytest.mark.parametrize("variant", ["nabeshima", "lageweg"])
+@pytest.mark.parametrize("inst", [14, 21])
+def test_pfsp_lb2_variants(golden_dir, variant, inst):
+    """LB2_NABESHIMA / LB2_LAGEWEG are pair tables handed to tsb_pfsp_create; bounds against the
+    reference's C code compiled with that variant (tests/golden/pfsp_f4.npz) and against the oracle"""
+    gold = np.load(os.path.join(golden_dir, "pfsp_f4.npz"))
+    tag = f"{variant}_ta{inst:03d}"
+    parents = gold[f"{tag}_parents"].view(tsb200.PFSP_NODE_DTYPE)
+    best = int(tsb200.lib().tsb_taillard_best_ub(inst))
+    with tsb200.PfspEvaluator(tables=tsb200.taillard_tables(inst, variant), M=4096) as ev:
+        assert ev.tables.pairs == ev.machines - 1
+        live = po.pfsp_live_mask(parents.view(po.PFSP_NODE_DTYPE), ev.jobs)
+        for b, key in ((best, "lb2_best"), (INT_MAX, "lb2_inf")):
+            got = ev.evaluate(parents, "lb2", b).reshape(-1, ev.jobs)
+            np.testing.assert_array_equal(got[live], gold[f"{tag}_{key}"].reshape(-1, ev.jobs)[live], err_msg=key)
+        rng = np.random.default_rng(inst)
+        check_pfsp(ev, rand_pfsp(rng, ev.jobs, 4096), "lb2", best)
+        check_pfsp(ev, rand_pfsp(rng, ev.jobs, 1000), "lb1", best)
+
+
+@pytest.mark.parametrize("inst", [31, 41, 51])
+def test_pfsp_max_jobs_50(golden_dir, inst):
+    """a MAX_JOBS = 50 handle (208-byte nodes): lb1 / lb1_d / lb2 on ta031 / ta041 / ta051 against the
+    reference's C code compiled with MAX_JOBS 50 (tests/golden/pfsp_f4.npz) and against the oracle built that way"""
+    from oracle import pyoracle50 as po50
+    gold = np.load(os.path.join(golden_dir, "pfsp_f4.npz"))
+    tag = f"jobs50_ta{inst:03d}"
+    parents = gold[f"{tag}_parents"].view(tsb200.PFSP_NODE50_DTYPE)
+    best = int(tsb200.lib().tsb_taillard_best_ub(inst))
+    t = po50.tables(inst)
+    with tsb200.PfspEvaluator(inst, M=5000) as ev:
+        assert ev.wide and ev.jobs == 50
+        live = po50.pfsp_live_mask(parents.view(po50.PFSP_NODE_DTYPE), 50)
+        for lb, key, b in (("lb1", "lb1", best), ("lb1_d", "lb1_d", best), ("lb2", "lb2_best", best), ("lb2", "lb2_inf", INT_MAX)):
+            got = ev.evaluate(parents, lb, b).reshape(-1, 50)
+            np.testing.assert_array_equal(got[live], gold[f"{tag}_{key}"].reshape(-1, 50)[live], err_msg=key)
+        # seeded random chunks (ragged sizes, every depth, the root for lb1_d) against the oracle
+        rng = np.random.default_rng(inst)
+        for count in (1, 63, 64, 65, 3000):
+            nodes = np.zeros(count, dtype=tsb200.PFSP_NODE50_DTYPE)
+            depth = rng.integers(0, 50, size=count)
+            nodes["depth"], nodes["limit1"] = depth, depth - 1
+            nodes["prmu"] = np.argsort(rng.random((count, 50)), axis=1).astype(np.int32)
+            live = po50.pfsp_live_mask(nodes.view(po50.PFSP_NODE_DTYPE), 50)
+            for lb, b in (("lb1_d", best), ("lb1", best)) + ((("lb2", best), ("lb2", 2**63 - 1)) if count <= 65 or inst != 51 else ()):
+                if lb != "lb1_d":
+                    use = nodes[nodes["limit1"] >= 0]  # lb1 / lb2 never see the root (SURVEY A.1)
+                else:
+                    use = nodes
+                if use.shape[0] == 0:
+                    continue
+                got = ev.evaluate(np.ascontiguousarray(use), lb, b).reshape(-1, 50)
+                want = po50.pfsp_evaluate(t, tsb200.LB_NAMES[lb], np.ascontiguousarray(use).view(po50.PFSP_NODE_DTYPE), min(b, 2**62)).reshape(-1, 50)
+                lv = po50.pfsp_live_mask(use.view(po50.PFSP_NODE_DTYPE), 50)
+                np.testing.assert_array_equal(got[lv], want[lv], err_msg=f"{lb} count={count}")
+        # the fused expand / pool entry points are 20-job only
+        with pytest.raises(tsb200.TsbError):
+            ev.pool_push(parents[:1].view(tsb200.PFSP_NODE_DTYPE)[:1])

@@ -95,3 +95,26 @@ def test_chapel_binding_declares_only_exported_symbols_with_matching_arity():
         assert name in decls, f"{name} is not declared in include/tsb200.h"
         n = 0 if not args.strip() else args.count(",") + 1
         assert n == decls[name], f"{name}: {n} parameters in TSB200.chpl, {decls[name]} in the header"
+
+
+@pytest.mark.parametrize("variant", ["full", "nabeshima", "lageweg", "learn"])
+@pytest.mark.parametrize("inst", [3, 14, 21])
+def test_host_tables_lb2_variants_equal_oracle(inst, variant):
+    t = tsb200.taillard_tables(inst, variant)
+    o = po.tables(inst, 0, po.LB2_VARIANTS[variant])
+    assert (t.jobs, t.machines, t.pairs) == (o.jobs, o.machines, o.pairs)
+    for name in ("lags", "mp0", "mp1", "mp_order", "johnson"):
+        np.testing.assert_array_equal(np.ctypeslib.as_array(getattr(t, name)), o.arr(name), err_msg=name)
+
+
+@pytest.mark.parametrize("inst", [31, 41, 51, 60])
+def test_host_tables50_equal_oracle50(inst):
+    """tables of the 50-job instances (a MAX_JOBS = 50 build) against the oracle built that way"""
+    from oracle import pyoracle50 as po50
+    t = tsb200.taillard_tables50(inst)
+    o = po50.tables(inst, heads_mode=0)
+    assert (t.jobs, t.machines, t.pairs) == (o.jobs, o.machines, o.pairs) and t.jobs == 50
+    for name in ("p_times", "min_heads", "min_tails", "lags", "mp0", "mp1", "mp_order", "johnson"):
+        np.testing.assert_array_equal(np.ctypeslib.as_array(getattr(t, name)), o.arr(name), err_msg=name)
+    with pytest.raises(tsb200.TsbError):
+        tsb200.taillard_tables(inst)  # does not fit a MAX_JOBS = 20 build
