@@ -380,4 +380,4 @@ def test_pfsp_max_jobs_50(golden_dir, inst):
                 np.testing.assert_array_equal(got[lv], want[lv], err_msg=f"{lb} count={count}")
         # the fused expand / pool entry points are 20-job only
         with pytest.raises(tsb200.TsbError):
-            ev.pool_push(parents[:1].view(tsb200.PFSP_NODE_DTYPE)[:1])
+            ev.pool_push(np.zeros(1, dtype=tsb200.PFSP_NODE_DTYPE))
