@@ -610,6 +610,11 @@ def main():
     world = dist_init("nccl")
     device_index = local_rank if world > 1 else 0
     peak, peak_src = peaks()
+    numa_cores = None
+    if world > 1:  # one process per GPU: run (and first-touch the host buffers) on the cores next to that GPU
+        import tsb200
+        rc = tsb200.lib().tsb_bind_thread_to_device(device_index)
+        numa_cores = rc if rc > 0 else None
 
     # ------------------------------------------------------------------ headline: the N=17 --M 50000 search
     if world == 1:
@@ -640,6 +645,8 @@ def main():
                                      "is bound by the two L2 flag exchanges (+ one release fence) that order it after "
                                      "the previous round (tools/flag_exchange.py), not by HBM — see kernels.* for "
                                      "the bandwidth-bound kernels"},
+                "numa": {"rank0_bound_to_cores_of_its_gpu": numa_cores, "note": "tsb_bind_thread_to_device: every rank (and "
+                         "every per-GPU host thread of the multi-GPU search) is pinned to the cores local to its GPU"},
                 "headline": {"explored_tree": GOLDEN_NQ[N_HEAD][0], "explored_sol": GOLDEN_NQ[N_HEAD][1],
                              "counts_match_reference": True, "offloads_per_search": h["offloads"],
                              "launches_per_search": h["launches_per_step"], "handle_create_ms": h["create_ms"],
