@@ -35,7 +35,7 @@ constexpr int RND_PPT = 2;                         // parents per thread
 constexpr int RND_SLICE = RND_THREADS * RND_PPT;   // parents per CTA per round at the default CTA size
 constexpr int RND_MAX_CTAS = 256;
 
-enum { RND_EXIT_DONE = 0, RND_EXIT_PAUSE = 1, RND_EXIT_SPACE = 2, RND_EXIT_ABORT = 3 };
+enum { RND_EXIT_DONE = 0, RND_EXIT_PAUSE = 1, RND_EXIT_SPACE = 2, RND_EXIT_ABORT = 3, RND_EXIT_RELAUNCH = 4 };
 
 // device-resident synchronisation area (zeroed once; epochs increase monotonically across launches)
 struct RoundsSync {

@@ -15,17 +15,19 @@
 // store -> L2 -> poll hop for the nodes.  Epochs are 32 bits and never repeat, so stale words cannot alias.
 //
 // Nodes that are NOT children of the previous round (the chunk reaches below the newest layer when a round produced
-// fewer than M children) were stored at least two rounds earlier.  For those, every CTA runs a FENCE WARP off the
-// critical path: it watches a shared-memory word the workers bump after each round's stores, executes the gpu-scope
-// fence and publishes fence_done[cta] = epoch; a reader of old nodes first checks that every CTA has fenced the
-// round before the previous one (normally long true: one sweep of 98 flags).
+// fewer than M children) carry the epoch of the round that stored them.  Every CTA keeps the LAYER STACK of the pool
+// — (first position, epoch) of every round's children that are still in the pool, a deterministic function of the
+// round totals like the rest of the pool state — and validates every piece against the epoch of the layer its
+// position lies in.  Nodes that were in the pool when the kernel was launched form one trusted layer (a kernel
+// boundary orders them).  (A first version fenced old rounds with a side warp and checked per-CTA fence flags before
+// reading old nodes: 1 300 cycles on the critical path of every round that reaches below the newest layer.)
 //
 // Measured alternatives for the one remaining exchange (all ~130 CTAs polling the 2 G count words: 2 500-4 000 cycles):
 // a dedicated aggregator CTA that scans the counts and writes every worker its own result line (two contention-free
 // hops: 2 900-3 400 cycles, no gain), per-reader rows that only their owner polls (no gain at 128 CTAs), CTAs of 512
 // threads (slower scan), fewer CTAs (cheaper exchange, more work per CTA: best at 128 of 148 SMs).
 //
-// The worker/fence split uses named barriers (bar.sync 1, T) for the workers; the plain 21-byte arena is converted
+// The plain 21-byte arena is converted
 // to and from the fat arena by nq_fat_import / nq_fat_export (whole pool, only when the host needs the plain form:
 // drain, steal, pool_step, arena growth).
 #pragma once
@@ -33,18 +35,19 @@
 
 namespace tsb {
 
-constexpr int LL_T = 256;                    // worker threads per CTA (+ 32: the fence warp)
+constexpr int LL_T = 256;                    // threads per CTA
 constexpr int LL_PPT = 2;                    // parents per worker thread
 constexpr int LL_SLICE = LL_T * LL_PPT;      // parents per CTA per round
 constexpr int LL_CAP = 2048;                 // children per window of the staging buffer
 constexpr int LL_WORDS = 8;                  // 8-byte words per fat node
+constexpr int LL_LAYERS = 1024;              // layers of the pool a CTA tracks (more: the kernel leaves and is relaunched)
+constexpr unsigned LL_TRUSTED = 0u;          // layer epoch of the nodes that were in the pool at launch (epochs start at 1)
 
 struct FatNode {
   unsigned long long w[LL_WORDS];
 };
 struct LlSync {
   unsigned long long slot[2][2 * RND_MAX_CTAS];  // by round parity, one per SUB-slice: epoch << 32 | leaves << 20 | children
-  unsigned fence_done[RND_MAX_CTAS];         // the CTA's stores of all rounds up to this epoch are fenced
   unsigned abort;
 };
 struct LlParams {
@@ -59,7 +62,7 @@ struct LlParams {
   RoundsState* state;
 };
 
-// ---- worker-only CTA barriers (the fence warp does not take part)
+// ---- CTA barriers on a named barrier (kept from the version that had a side warp outside them)
 __device__ __forceinline__ void ll_bar(int threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
 __device__ __forceinline__ bool ll_bar_or(int threads, bool pred) {
   uint32_t r;
@@ -148,8 +151,8 @@ struct LlSmem {
   alignas(16) uint16_t item[T * LL_PPT * 20];  // (record << 5) | slot, in child order
   unsigned long long warp_tot64[T / 32];
   unsigned long long red[3];
-  unsigned stored_epoch;  // workers -> fence warp: all stores of rounds up to this epoch have been issued
-  unsigned fence_exit;
+  long long lay_start[LL_LAYERS];  // the pool's layers, bottom to top: first position ...
+  unsigned lay_epoch[LL_LAYERS];   // ... and the epoch its nodes were stored with (LL_TRUSTED: before the launch)
 };
 
 // child `item` of the slice (pure data: no alignment games in the fat format) -> its eight data words
@@ -184,7 +187,7 @@ __device__ __forceinline__ void ll_build_child(const uint32_t (*parent)[8], int 
 }
 
 template <int N, int T>
-__global__ void __launch_bounds__(T + 32, 1) nq_rounds_ll_kernel(const __grid_constant__ LlParams prm) {
+__global__ void __launch_bounds__(T, 1) nq_rounds_ll_kernel(const __grid_constant__ LlParams prm) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   LlSmem<T>& sm = *reinterpret_cast<LlSmem<T>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -193,38 +196,15 @@ __global__ void __launch_bounds__(T + 32, 1) nq_rounds_ll_kernel(const __grid_co
   FatNode* const fat = prm.fat;
 
   if (t == 0) {
-    sm.stored_epoch = prm.epoch0;
-    sm.fence_exit = 0;
+    sm.lay_start[0] = 0;
+    sm.lay_epoch[0] = LL_TRUSTED;
   }
-  __syncthreads();  // (the only barrier all T + 32 threads take)
-
-  // ------------------------------------------------------------------------------------------ the fence warp
-  if (t >= T) {
-    if (lane == 0) {
-      unsigned done = prm.epoch0;  // everything up to epoch0 was stored before the launch
-      *reinterpret_cast<volatile unsigned*>(&sy->fence_done[k]) = done;
-      for (;;) {
-        unsigned e, x;
-        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(e) : "r"(smem_u32(&sm.stored_epoch)) : "memory");
-        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(x) : "r"(smem_u32(&sm.fence_exit)) : "memory");
-        if (e != done) {
-          __threadfence();  // cumulative: orders the workers' stores (observed through the shared word) gpu-wide
-          *reinterpret_cast<volatile unsigned*>(&sy->fence_done[k]) = e;
-          done = e;
-        } else if (x) {
-          break;
-        } else {
-          __nanosleep(64);
-        }
-      }
-    }
-    return;
-  }
+  __syncthreads();
+  int n_lay = prm.size0 > 0 ? 1 : 0;
 
   // ------------------------------------------------------------------------------------------ the workers
   long long size = prm.size0;
   unsigned epoch = prm.epoch0;
-  long long layer_start = prm.size0;  // positions >= layer_start were written in the previous round (none yet)
   unsigned long long rounds = 0, tot_parents = 0, tot_children = 0, tot_solutions = 0;
   int exit_code = RND_EXIT_PAUSE;
   long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = 0;
@@ -252,7 +232,10 @@ __global__ void __launch_bounds__(T + 32, 1) nq_rounds_ll_kernel(const __grid_co
       exit_code = RND_EXIT_SPACE;
       break;
     }
-    const unsigned prev_epoch = epoch;  // the tag of the children of the previous round
+    if (n_lay >= LL_LAYERS) {  // (no room to record this round's children: start over with one trusted layer)
+      exit_code = RND_EXIT_RELAUNCH;
+      break;
+    }
     ++epoch;
     if (prof_on) tp = clock64();
     // my share of the chunk: TWO sub-slices of n / 2G parents — number k from the bottom and number k from the top.
@@ -260,51 +243,23 @@ __global__ void __launch_bounds__(T + 32, 1) nq_rounds_ll_kernel(const __grid_co
     // CTA left the bottom CTA with 3x the average children, and its build + 64-byte stores were the round's
     // critical path; pairing k with 2G-1-k evens the load without knowing it in advance.
     const int G2 = 2 * G;
-    const int a0 = static_cast<int>(n * k / G2), len0 = static_cast<int>(n * (k + 1) / G2) - a0;
-    const int a1 = static_cast<int>(n * (G2 - 1 - k) / G2), len1 = static_cast<int>(n * (G2 - k) / G2) - a1;
+    const unsigned n32 = static_cast<unsigned>(n), uG2 = static_cast<unsigned>(G2), uk = static_cast<unsigned>(k);
+    // (n <= 512 G and k < G <= 256: the products fit 32 bits — four 64-bit divisions cost 700 cycles per round)
+    const int a0 = static_cast<int>(n32 * uk / uG2), len0 = static_cast<int>(n32 * (uk + 1u) / uG2) - a0;
+    const int a1 = static_cast<int>(n32 * (uG2 - 1u - uk) / uG2), len1 = static_cast<int>(n32 * (uG2 - uk) / uG2) - a1;
     const int len = len0 + len1;
 
-    // ---- (1) old nodes in my share (stored two or more rounds ago): every CTA has fenced those rounds
     bool ok = true;
-    const bool has_old = (len0 > 0 && s0 + a0 < layer_start) || (len1 > 0 && s0 + a1 < layer_start);
-    if (has_old && wid == 0) {
-      const unsigned need = prev_epoch - 1u;  // (for r == 0: epoch0 - 1 < epoch0, published at kernel start)
-      SpinGuard guard;
-      for (;;) {
-        bool good = true;
-        for (int i = 4 * lane; i < G; i += 128) {
-          unsigned v0, v1, v2, v3;
-          asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
-                       : "l"(sy->fence_done + i)
-                       : "memory");
-          // (epochs only grow; signed distance keeps the comparison right across a 32-bit wrap)
-          good &= static_cast<int>(v0 - need) >= 0 && (i + 1 >= G || static_cast<int>(v1 - need) >= 0) &&
-                  (i + 2 >= G || static_cast<int>(v2 - need) >= 0) && (i + 3 >= G || static_cast<int>(v3 - need) >= 0);
-        }
-        if (__all_sync(0xFFFFFFFFu, good)) break;
-        if (__any_sync(0xFFFFFFFFu, guard.expired(&sy->abort))) {
-          ok = false;
-          break;
-        }
-      }
-    }
-    if (has_old) {  // (block-uniform: a, s0, layer_start are)
-      if (ll_bar_or(T, !ok)) {
-        exit_code = RND_EXIT_ABORT;
-        break;
-      }
-    }
     TSB_PROF(0)
 
     // ---- (2) my slice -> shared memory, 16-byte piece by piece (4 pieces per node, consecutive lanes on consecutive
-    // pieces: every warp load is 512 contiguous bytes); a piece of a NEW node is polled until both of its words
-    // carry the previous round's epoch
+    // pieces: every warp load is 512 contiguous bytes); a piece is polled until both of its words carry the epoch of
+    // the layer its node lies in
     {
       SpinGuard guard;
       const unsigned long long* src0 = fat[s0 + a0].w;
       const unsigned long long* src1 = fat[s0 + a1].w - 8 * len0;  // (indexed by the concatenated piece number)
-      const long long new0 = layer_start - (s0 + a0), new1 = layer_start - (s0 + a1) + len0;  // first new node index
+      const int top = n_lay - 1;
       constexpr int PCS = 4 * LL_PPT;  // pieces per thread
       unsigned long long w0[PCS], w1[PCS];
       unsigned pending = 0;
@@ -322,10 +277,14 @@ __global__ void __launch_bounds__(T + 32, 1) nq_rounds_ll_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < PCS; j++)
           if (pending & (1u << j)) {
-            const int pc = t + j * T;
-            const bool is_new = (pc >> 2) >= ((pc >> 2) < len0 ? new0 : new1);
-            if (!is_new || (static_cast<unsigned>(w0[j] >> 32) == prev_epoch && static_cast<unsigned>(w1[j] >> 32) == prev_epoch)) {
-              *reinterpret_cast<uint2*>(&sm.parent[pc >> 2][2 * (pc & 3)]) =
+            const int pc = t + j * T, i = pc >> 2;
+            // the epoch this node was stored with: that of the layer its position lies in (mostly the top one)
+            const long long pos = s0 + (i < len0 ? a0 + i : a1 + (i - len0));
+            int L = top;
+            while (L > 0 && sm.lay_start[L] > pos) --L;
+            const unsigned want = sm.lay_epoch[L];
+            if (want == LL_TRUSTED || (static_cast<unsigned>(w0[j] >> 32) == want && static_cast<unsigned>(w1[j] >> 32) == want)) {
+              *reinterpret_cast<uint2*>(&sm.parent[i][2 * (pc & 3)]) =
                   make_uint2(static_cast<uint32_t>(w0[j]), static_cast<uint32_t>(w1[j]));
               pending &= ~(1u << j);
             }
@@ -457,19 +416,30 @@ __global__ void __launch_bounds__(T + 32, 1) nq_rounds_ll_kernel(const __grid_co
       }
     }
     TSB_PROF(4)
-    // ---- (8) tell the fence warp (off the critical path): stores of rounds up to `epoch` are issued
-    ll_bar(T);
-    if (t == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&sm.stored_epoch)), "r"(epoch) : "memory");
+    // ---- (8) the pool's layers after the round: every layer that starts inside the chunk is consumed, the round's
+    // children form the new top layer (same computation in every CTA)
+    {
+      int nl = n_lay;
+      while (nl > 0 && sm.lay_start[nl - 1] >= s0) --nl;
+      ll_bar(T);  // (everybody has read the old entries, the window buffers and sm.red)
+      if (round_children > 0) {
+        if (t == 0) {
+          sm.lay_start[nl] = s0;
+          sm.lay_epoch[nl] = epoch;
+        }
+        ++nl;
+      }
+      n_lay = nl;
+      ll_bar(T);
+    }
     TSB_PROF(5)
     // ---- (9) the pool after the round
-    layer_start = s0;
     size = s0 + round_children;
     ++rounds;
     tot_parents += static_cast<unsigned long long>(n);
     tot_children += static_cast<unsigned long long>(round_children);
     tot_solutions += static_cast<unsigned long long>(round_leaves);
   }
-  if (t == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&sm.fence_exit)), "r"(1u) : "memory");
   if (k == 0 && t == 0) {
     RoundsState* st = prm.state;
     st->size = size;

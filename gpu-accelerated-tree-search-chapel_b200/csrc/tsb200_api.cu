@@ -1351,7 +1351,7 @@ int nq_ll_launch_n(tsb_nq* h, const tsb::LlParams& prm, int grid, cudaStream_t s
     h->rounds.attr_ll = true;
   }
   void* args[] = {const_cast<tsb::LlParams*>(&prm)};
-  TSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid), dim3(tsb::LL_T + 32), args, smem, s));
+  TSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid), dim3(tsb::LL_T), args, smem, s));
   h->launches++;
   return TSB_OK;
 }
@@ -1506,6 +1506,7 @@ int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rou
         if (rc != TSB_OK) return rc;
         continue;
       }
+      if (st.exit_code == tsb::RND_EXIT_RELAUNCH) continue;  // (layer table full: a fresh launch trusts the whole pool)
       break;  // DONE or PAUSE
     }
     return TSB_OK;
