@@ -236,4 +236,55 @@ __global__ void __launch_bounds__(T) nq_evaluate_kernel(const uint8_t* __restric
       [](const uint8_t* in_tile, uint8_t* out_tile, int n, long long) { nq_compute_tile<N, VAR>(in_tile, out_tile, n); });
 }
 
+// ---- small chunks (the reference's default --M 50000 is 97 tiles of 512 parents: two thirds of the SMs, each thread
+// working through four parents, behind a TMA pipeline set up for one tile): one parent per thread, 128 parents per
+// CTA, plain coalesced 16-byte loads and stores — the shortest path from launch to labels.  The chunk's tail reads
+// at most 15 bytes past the last record (as the TMA path does).
+__device__ __forceinline__ void nq_parent_words(const uint8_t* src, uint32_t (&P)[6]) {  // any byte alignment
+  const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src)) & 3u, a8 = mis * 8u;
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - mis);
+  const uint32_t s0 = sw[0], s1 = sw[1], s2 = sw[2], s3 = sw[3], s4 = sw[4], s5 = sw[5];
+  P[0] = shf_r_wrap(s0, s1, a8);
+  P[1] = shf_r_wrap(s1, s2, a8);
+  P[2] = shf_r_wrap(s2, s3, a8);
+  P[3] = shf_r_wrap(s3, s4, a8);
+  P[4] = shf_r_wrap(s4, s5, a8);
+  P[5] = shf_r_wrap(s5, 0u, a8);
+}
+constexpr int NQ_SMALL = 128;  // parents per CTA
+template <int N>
+__global__ void __launch_bounds__(NQ_SMALL) nq_evaluate_small_kernel(const uint8_t* __restrict__ parents,
+                                                                    uint8_t* __restrict__ labels, int count) {
+  __shared__ __align__(16) uint8_t in[NQ_SMALL * NQ_REC + 32];
+  __shared__ __align__(16) uint8_t out[NQ_SMALL * N + 16];
+  const int t = threadIdx.x;
+  const int p0 = blockIdx.x * NQ_SMALL;
+  const int np = min(NQ_SMALL, count - p0);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(parents + static_cast<size_t>(p0) * NQ_REC);  // 128 * 21 = 168 * 16
+    uint4* dst = reinterpret_cast<uint4*>(in);
+    for (int i = t; i < (np * NQ_REC + 15) / 16; i += NQ_SMALL) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (t < np) {
+    uint32_t P[6];
+    nq_parent_words(in + t * NQ_REC, P);
+    NqParent<N, 0, 0> p;
+    p.init(P);
+    if (p.depth > 0u) p.template rows<0, 4>();
+    if (p.depth > 4u) p.template rows<4, 8>();
+    if (p.depth > 8u) p.template rows<8, 12>();
+    if (p.depth > 12u) p.template rows<12, 16>();
+    if (p.depth > 16u) p.template rows<16, 20>();
+    const uint32_t S = ~p.U;
+#pragma unroll
+    for (int k = 0; k < N; k++) out[t * N + k] = static_cast<uint8_t>(shf_r_wrap(S, 0u, p.amt[k]) & 1u);
+  }
+  __syncthreads();
+  uint8_t* dst = labels + static_cast<size_t>(p0) * N;  // 128 * N: a multiple of 16
+  const int bytes = np * N, n16 = bytes >> 4;
+  for (int i = t; i < n16; i += NQ_SMALL) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(out)[i];
+  for (int i = 16 * n16 + t; i < bytes; i += NQ_SMALL) dst[i] = out[i];
+}
+
 }  // namespace tsb

@@ -538,7 +538,7 @@ struct tsb_nq : Base {
   int N = 0, g = 1;
   RoundsCtx rounds;
   int variant = 0;  // env TSB200_NQ_VARIANT (kernel A/B experiments)
-  int tile_threads = 0;  // env TSB200_NQ_TILE_THREADS = 128 | 64: force the tile size (A/B experiments)
+  int tile_threads = 0;  // env TSB200_NQ_TILE_THREADS = 128: always the TMA-pipelined kernel (A/B experiments)
   int occ[3] = {0, 0, 0};  // cached CTAs per SM, per tile size (128 / 64 / 32 threads)
   bool attr_set[3] = {false, false, false};
   // fused expand (evaluate + generate_children on the device) and the device-resident pool
@@ -568,18 +568,20 @@ int launch_nq_nt(tsb_nq* h, int slot, const uint8_t* in, uint8_t* out, long long
   h->launches++;
   return TSB_OK;
 }
-// tile size by count: a chunk should make at least ~2 tiles per SM (at the reference's default --M 50000 tiles
-// of 512 parents would occupy 97 of the 148 SMs)
+// small chunks (fewer than two 512-parent tiles per SM — the reference's default --M 50000 is 97 tiles) take the
+// one-parent-per-thread kernel, everything else the TMA-pipelined one
 template <int N, int VAR>
 int launch_nq_n(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
-  const long long want = 2LL * h->di.sms;
-  if (count / (128 * tsb::NQ_QUAD) >= want || h->tile_threads == 128) return launch_nq_nt<N, VAR, 128>(h, 0, in, out, count, s);
   if constexpr (VAR == 0) {
-    if (count / (64 * tsb::NQ_QUAD) >= want || h->tile_threads == 64) return launch_nq_nt<N, VAR, 64>(h, 1, in, out, count, s);
-    return launch_nq_nt<N, VAR, 32>(h, 2, in, out, count, s);
-  } else {
-    return launch_nq_nt<N, VAR, 128>(h, 0, in, out, count, s);
+    if (count < 2LL * h->di.sms * tsb::NQ_TILE && h->tile_threads != 128) {
+      const int grid = static_cast<int>((count + tsb::NQ_SMALL - 1) / tsb::NQ_SMALL);
+      tsb::nq_evaluate_small_kernel<N><<<grid, tsb::NQ_SMALL, 0, s>>>(in, out, static_cast<int>(count));
+      TSB_CUDA(cudaGetLastError());
+      h->launches++;
+      return TSB_OK;
+    }
   }
+  return launch_nq_nt<N, VAR, 128>(h, 0, in, out, count, s);
 }
 
 int launch_nq(tsb_nq* h, const uint8_t* in, uint8_t* out, long long count, cudaStream_t s) {
