@@ -205,8 +205,14 @@ struct StealBoard {
 };
 
 // what a device-pool task does between two launches: publish its pool size, serve a pending steal request
+// smallest pool worth stealing from: the reference's 2 m (Pool_par.chpl:178-191) for the small chunks of the
+// persistent kernel; with large chunks a pool below 2 M is one or two bandwidth-bound rounds of work — splitting
+// it costs more (arena reservation on the thief, under-filled launches on both) than it saves: on 8 GPUs the
+// N=17 search at M = 4 Mi went from 0.06 s (static split) to 0.18 s when every idle task stole half of such pools
+inline long long steal_floor(int m, int M) { return M <= 75776 ? 2LL * m : std::max<long long>(2LL * m, 2LL * M); }
+
 template <class StealFn>
-int board_service(StealBoard* sb, int me, long long my_size, int m, StealFn&& steal) {
+int board_service(StealBoard* sb, int me, long long my_size, long long floor_, StealFn&& steal) {
   if (!sb) return TSB_OK;
   int thief = -1;
   {
@@ -218,7 +224,7 @@ int board_service(StealBoard* sb, int me, long long my_size, int m, StealFn&& st
   if (thief < 0) return TSB_OK;
   int64_t got = 0;
   int rc = TSB_OK;
-  if (my_size >= 2LL * m && !sb->failed) rc = steal(sb->handle[me], sb->handle[thief], &got);
+  if (my_size >= floor_ && !sb->failed) rc = steal(sb->handle[me], sb->handle[thief], &got);
   {
     std::lock_guard<std::mutex> lk(sb->mu);
     sb->reply[thief] = (rc == TSB_OK && got > 0) ? 1 : -1;
@@ -229,7 +235,7 @@ int board_service(StealBoard* sb, int me, long long my_size, int m, StealFn&& st
   return rc;
 }
 // out of work: true = stole something (keep going), false = everybody is idle (terminate)
-inline bool board_acquire(StealBoard* sb, int me, long long my_size, int m) {
+inline bool board_acquire(StealBoard* sb, int me, long long my_size, long long floor_) {
   if (!sb) return false;
   std::unique_lock<std::mutex> lk(sb->mu);
   sb->size[me] = my_size;
@@ -251,7 +257,7 @@ inline bool board_acquire(StealBoard* sb, int me, long long my_size, int m) {
     if (sb->done) return false;
     int v = -1;
     for (int i = 0; i < sb->D && !sb->failed; i++)  // the fullest pool nobody is already asking
-      if (i != me && sb->request[i] < 0 && sb->size[i] >= 2LL * m && (v < 0 || sb->size[i] > sb->size[v])) v = i;
+      if (i != me && sb->request[i] < 0 && sb->size[i] >= floor_ && (v < 0 || sb->size[i] > sb->size[v])) v = i;
     if (v < 0) {
       deny_mine();
       sb->cv.wait_for(lk, std::chrono::microseconds(200));
@@ -264,7 +270,7 @@ inline bool board_acquire(StealBoard* sb, int me, long long my_size, int m) {
     if (sb->reply[me] > 0) return true;
     if (sb->done) return false;
     ++sb->idle;
-    sb->size[v] = std::min<long long>(sb->size[v], 2LL * m - 1);  // (it publishes again after its next launch)
+    sb->size[v] = std::min<long long>(sb->size[v], floor_ - 1);  // (it publishes again after its next launch)
   }
 }
 
@@ -297,10 +303,10 @@ void nq_devpool_rounds(tsb_nq* h, int m, int M, StealBoard* sb, int me, GpuTaskR
     r.parents += np;
     const long long size = tsb_nq_pool_size(h);
     if (size >= m) {
-      r.rc = board_service(sb, me, size, m, steal);
+      r.rc = board_service(sb, me, size, steal_floor(m, M), steal);
       continue;
     }
-    if (!board_acquire(sb, me, size, m)) break;
+    if (!board_acquire(sb, me, size, steal_floor(m, M))) break;
   }
   if (r.rc != TSB_OK) board_abort(sb, me);
 }
@@ -533,7 +539,7 @@ void pfsp_devpool_on(tsb_pfsp* h, int lb_kind, int m, int M, Pool<tsb_pfsp_node>
     r.rc = tsb_pfsp_pool_step(h, lb_kind, m, M, &r.best, &np, &nc, &ns);
     if (r.rc != TSB_OK) break;
     if (np == 0) {
-      if (!board_acquire(sb, me, tsb_pfsp_pool_size(h), m)) break;
+      if (!board_acquire(sb, me, tsb_pfsp_pool_size(h), steal_floor(m, M))) break;
       continue;
     }
     r.tree += nc;
@@ -542,7 +548,7 @@ void pfsp_devpool_on(tsb_pfsp* h, int lb_kind, int m, int M, Pool<tsb_pfsp_node>
     r.parents += static_cast<uint64_t>(np);
     if (sb && ++since_service >= 2) {  // publish the pool size / serve thieves every other round
       since_service = 0;
-      r.rc = board_service(sb, me, tsb_pfsp_pool_size(h), m, steal);
+      r.rc = board_service(sb, me, tsb_pfsp_pool_size(h), steal_floor(m, M), steal);
     }
   }
   if (r.rc != TSB_OK) board_abort(sb, me);
