@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "nq_expand.cuh"
+#include "nq_expand2.cuh"
 #include "nq_rounds.cuh"
 #include "nq_rounds_ll.cuh"
 #include "pfsp_expand.cuh"
@@ -324,8 +325,8 @@ struct ExpandCtx {
   tsb::ExpandResult* h_res = nullptr;  // pinned + mapped: written by the scan kernel of a round
   tsb::ExpandResult* d_res = nullptr;  // device alias of h_res
   unsigned epoch = 0;
-  int occ_count = 0, occ_build = 0;
-  bool attr_set = false;
+  int occ_count = 0, occ_build = 0, occ_count2 = 0, occ_build2 = 0;
+  bool attr_set = false, attr_set2 = false;
   // (clears are ordered on the stream the kernels run on: the handle's streams do not synchronise with the
   // legacy default stream)
   int reserve(long long tiles, long long side_bytes_per_tile, cudaStream_t s, int best_init = 0x7FFFFFFF) {
@@ -339,7 +340,8 @@ struct ExpandCtx {
       TSB_CUDA(cudaHostAlloc(&h_res, sizeof(tsb::ExpandResult), cudaHostAllocPortable | cudaHostAllocMapped));
       TSB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_res), h_res, 0));
     }
-    if (tiles > tile_cap || side_bytes_per_tile != side_bytes) {
+    if (tiles > tile_cap || side_bytes_per_tile > side_bytes) {
+      side_bytes_per_tile = std::max(side_bytes_per_tile, side_bytes);
       if (d_cmask) cudaFree(d_cmask);
       if (d_tile) cudaFree(d_tile);
       d_cmask = nullptr;
@@ -393,6 +395,9 @@ struct ExpandCtx {
 // copied; the holes left behind are reclaimed by compacting into the second arena when the top reaches the end.
 struct DevicePool {
   uint8_t* arena[2] = {nullptr, nullptr};
+  // optional side array: `side_rec` bytes per arena position, moved with the nodes (N-Queens: nq_expand2.cuh)
+  uint8_t* side[2] = {nullptr, nullptr};
+  size_t side_rec = 0, side_slack = 0;
   long long cap = 0;  // nodes per arena
   int cur = 0;
   size_t rec = 0, slack = 0;
@@ -401,34 +406,44 @@ struct DevicePool {
   uint64_t compactions = 0;
   long long top() const { return ext.empty() ? 0 : ext.back().e; }
   size_t bytes(long long nodes) const { return static_cast<size_t>(nodes) * rec + slack + 64; }
+  size_t side_bytes(long long nodes) const { return static_cast<size_t>(nodes) * side_rec + side_slack + 64; }
   int ensure_arena(int which, long long nodes) {
     (void)nodes;
     if (!arena[which]) TSB_CUDA(cudaMalloc(&arena[which], bytes(cap)));
+    if (side_rec && !side[which]) TSB_CUDA(cudaMalloc(&side[which], side_bytes(cap)));
     return TSB_OK;
   }
   // all extents -> [0, size) of the other arena (or of fresh, larger arenas when `new_cap` > cap)
   int compact(cudaStream_t s, long long new_cap) {
-    uint8_t* dst = nullptr;
+    uint8_t *dst = nullptr, *sdst = nullptr;
     const bool grow = new_cap > cap;
     if (grow) {
       TSB_CUDA(cudaMalloc(&dst, static_cast<size_t>(new_cap) * rec + slack + 64));
+      if (side_rec) TSB_CUDA(cudaMalloc(&sdst, side_bytes(new_cap)));
     } else {
       int rc = ensure_arena(cur ^ 1, cap);
       if (rc != TSB_OK) return rc;
       dst = arena[cur ^ 1];
+      sdst = side[cur ^ 1];
     }
     long long at = 0;
     for (const PoolExtent& x : ext) {
       TSB_CUDA(cudaMemcpyAsync(dst + at * rec, arena[cur] + x.b * rec, static_cast<size_t>(x.e - x.b) * rec,
                                cudaMemcpyDeviceToDevice, s));
+      if (side_rec && side[cur])
+        TSB_CUDA(cudaMemcpyAsync(sdst + at * side_rec, side[cur] + x.b * side_rec,
+                                 static_cast<size_t>(x.e - x.b) * side_rec, cudaMemcpyDeviceToDevice, s));
       at += x.e - x.b;
     }
     TSB_CUDA(cudaStreamSynchronize(s));
     if (grow) {
-      if (arena[0]) cudaFree(arena[0]);
-      if (arena[1]) cudaFree(arena[1]);
+      for (int i = 0; i < 2; i++) {
+        if (arena[i]) cudaFree(arena[i]);
+        if (side[i]) cudaFree(side[i]);
+        arena[i] = side[i] = nullptr;
+      }
       arena[0] = dst;
-      arena[1] = nullptr;
+      side[0] = sdst;
       cur = 0;
       cap = new_cap;
     } else {
@@ -451,9 +466,11 @@ struct DevicePool {
     return compact(s, need > cap ? std::max<long long>(2 * cap, need + need / 2) : cap);
   }
   void release() {
-    if (arena[0]) cudaFree(arena[0]);
-    if (arena[1]) cudaFree(arena[1]);
-    arena[0] = arena[1] = nullptr;
+    for (int i = 0; i < 2; i++) {
+      if (arena[i]) cudaFree(arena[i]);
+      if (side[i]) cudaFree(side[i]);
+      arena[i] = side[i] = nullptr;
+    }
     ext.clear();
     size = 0;
     cap = 0;
@@ -535,6 +552,7 @@ struct RoundsCtx {
 };
 
 struct tsb_nq : Base {
+  bool aux_ok = false;  // every node of the pool has its side word (nq_expand2.cuh)
   int N = 0, g = 1;
   RoundsCtx rounds;
   int variant = 0;  // env TSB200_NQ_VARIANT (kernel A/B experiments)
@@ -626,9 +644,11 @@ int make_params(const std::vector<PoolExtent>& pieces, int tile_records, tsb::Ex
 
 // one evaluate + generate_children round over `pieces` of `arena` (count, build); children packed at
 // `children_d`.  Synchronous: the counts come back through the host-mapped result record.
-template <int N>
-int nq_expand_n(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& pieces, uint8_t* children_d,
-                cudaStream_t s, unsigned long long* n_children, unsigned long long* n_solutions, bool early) {
+// AUX: `aux` / `children_aux` are the side arrays of `arena` / `children_d` (nq_expand2.cuh)
+template <int N, bool AUX>
+int nq_expand_n(tsb_nq* h, const uint8_t* arena, const unsigned long long* aux, const std::vector<PoolExtent>& pieces,
+                uint8_t* children_d, unsigned long long* children_aux, cudaStream_t s, unsigned long long* n_children,
+                unsigned long long* n_solutions, bool early) {
   tsb::ExpandParams prm;
   int rc = make_params(pieces, tsb::NQ_TILE, &prm);
   if (rc != TSB_OK) return rc;
@@ -640,26 +660,27 @@ int nq_expand_n(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& 
   rc = ex.reserve(std::max<long long>(prm.n_tiles, h->M_max / tsb::NQ_TILE + 2 * tsb::EXP_MAX_PIECES),
                   static_cast<long long>(tsb::NQ_TILE) * N * 2, s);
   if (rc != TSB_OK) return rc;
-  auto k1 = tsb::nq_expand_count_kernel<N>;
-  auto k3 = tsb::nq_expand_build_kernel<N>;
-  const size_t smem1 = sizeof(tsb::NqCountSmem) + 128, smem3 = sizeof(tsb::NqBuildSmem) + 128;
-  if (!ex.attr_set) {
+  auto k1 = tsb::nq_expand_count_kernel<N, AUX>;
+  auto k3 = tsb::nq_expand_build_kernel<N, AUX>;
+  const size_t smem1 = sizeof(tsb::NqCountSmem<AUX>) + 128, smem3 = sizeof(tsb::NqBuildSmem<AUX>) + 128;
+  bool& attr_set = AUX ? ex.attr_set2 : ex.attr_set;
+  if (!attr_set) {
     TSB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
     TSB_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem3)));
-    ex.attr_set = true;
+    attr_set = true;
   }
   const long long recs = static_cast<long long>(prm.n_tiles) * tsb::NQ_TILE;
   int g1 = 1, g3 = 1;
-  rc = grid_for(k1, tsb::NQ_THREADS, smem1, recs, tsb::NQ_TILE, h->di.sms, &g1, &ex.occ_count);
+  rc = grid_for(k1, tsb::NQ_THREADS, smem1, recs, tsb::NQ_TILE, h->di.sms, &g1, AUX ? &ex.occ_count2 : &ex.occ_count);
   if (rc != TSB_OK) return rc;
-  rc = grid_for(k3, tsb::NQ_THREADS, smem3, recs, tsb::NQ_TILE, h->di.sms, &g3, &ex.occ_build);
+  rc = grid_for(k3, tsb::NQ_THREADS, smem3, recs, tsb::NQ_TILE, h->di.sms, &g3, AUX ? &ex.occ_build2 : &ex.occ_build);
   if (rc != TSB_OK) return rc;
   prm.epoch = ++ex.epoch;
   if ((prm.n_tiles + g3 - 1) / g3 > tsb::EXP_MAX_OWN) return TSB_EINVAL;  // (M_max * N < 2^31 keeps this far away)
   uint16_t* d_items = reinterpret_cast<uint16_t*>(ex.d_cmask);
   const double tr1 = trace ? tnow() : 0;
-  k1<<<g1, tsb::NQ_THREADS, smem1, s>>>(arena, prm, d_items, ex.d_tile, ex.d_st);
-  k3<<<g3, tsb::NQ_THREADS, smem3, s>>>(arena, prm, d_items, ex.d_tile, children_d, ex.d_st, ex.d_res);
+  k1<<<g1, tsb::NQ_THREADS, smem1, s>>>(arena, aux, prm, d_items, ex.d_tile, ex.d_st);
+  k3<<<g3, tsb::NQ_THREADS, smem3, s>>>(arena, aux, prm, d_items, ex.d_tile, children_d, children_aux, ex.d_st, ex.d_res);
   TSB_CUDA(cudaGetLastError());
   h->launches += 2;
   const double tr2 = trace ? tnow() : 0;
@@ -677,11 +698,13 @@ int nq_expand_n(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& 
 }
 
 int nq_expand_dispatch(tsb_nq* h, const uint8_t* arena, const std::vector<PoolExtent>& pieces, uint8_t* children_d,
-                       cudaStream_t s, unsigned long long* nc, unsigned long long* ns, bool early = false) {
+                       cudaStream_t s, unsigned long long* nc, unsigned long long* ns, bool early = false,
+                       const unsigned long long* aux = nullptr, unsigned long long* children_aux = nullptr) {
   switch (h->N) {
-#define TSB_NQ_CASE(n) \
-  case n:              \
-    return nq_expand_n<n>(h, arena, pieces, children_d, s, nc, ns, early);
+#define TSB_NQ_CASE(n)                                                                                   \
+  case n:                                                                                                \
+    return aux ? nq_expand_n<n, true>(h, arena, aux, pieces, children_d, children_aux, s, nc, ns, early) \
+               : nq_expand_n<n, false>(h, arena, nullptr, pieces, children_d, nullptr, s, nc, ns, early);
     TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
     TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
     TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
@@ -1237,17 +1260,65 @@ int tsb_nq_expand(tsb_nq* h, const void* parents, int count, void* children, uin
   return h->copy_d2h(children, h->d_children, nc * sizeof(tsb_nq_node), h->stream);
 }
 
+}  // extern "C"
 namespace {
 // arena capacity a handle starts with: four worst-case rounds (every slot of every parent survives)
 long long nq_pool_min_cap(const tsb_nq* h) {
   if (const long long c = env_pool_cap(); c > 0) return c;
   return std::max<long long>(1LL << 22, 4LL * h->M_max * h->N);
 }
+// A/B experiment, off by default (TSB200_AUX=1 turns it on): one side word per node (nq_expand2.cuh).  Measured on
+// the N = 17 search at M = 4 Mi: count 36.8 us + build 59.9 us per round against 44.6 + 51.5 us without — the
+// instructions it saves in the count kernel are paid back as 38 % more bytes per node.
+bool env_aux() {
+  static const bool v = [] {
+    const char* e = std::getenv("TSB200_AUX");
+    return e && *e && *e != '0';
+  }();
+  return v;
+}
 void nq_pool_setup(tsb_nq* h) {
   h->pool.rec = sizeof(tsb_nq_node);
   h->pool.slack = static_cast<size_t>(tsb::NQ_TILE) * sizeof(tsb_nq_node);  // full-tile loads may run past the top
+  if (env_aux()) {
+    h->pool.side_rec = sizeof(unsigned long long);
+    h->pool.side_slack = static_cast<size_t>(tsb::NQ_TILE) * sizeof(unsigned long long);
+  }
+}
+template <int N>
+int nq_aux_fill_n(tsb_nq* h, long long lo, long long hi) {
+  if (hi <= lo) return TSB_OK;
+  const long long blocks = std::min<long long>((hi - lo + 255) / 256, 64LL * h->di.sms);
+  tsb::nq_aux_fill_kernel<N><<<static_cast<unsigned>(blocks), 256, 0, h->stream>>>(
+      h->pool.arena[h->pool.cur], reinterpret_cast<unsigned long long*>(h->pool.side[h->pool.cur]), lo, hi);
+  TSB_CUDA(cudaGetLastError());
+  h->launches++;
+  return TSB_OK;
+}
+int nq_aux_fill(tsb_nq* h, long long lo, long long hi) {
+  switch (h->N) {
+#define TSB_NQ_CASE(n) \
+  case n:              \
+    return nq_aux_fill_n<n>(h, lo, hi);
+    TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
+    TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
+    TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
+    TSB_NQ_CASE(20)
+#undef TSB_NQ_CASE
+  }
+  return TSB_EINVAL;
+}
+// side words for every node of the pool (after host pushes into a pool whose words were stale, a steal, the
+// persistent kernel's export)
+int nq_aux_ensure(tsb_nq* h) {
+  if (h->aux_ok || !h->pool.side_rec) return TSB_OK;
+  for (const PoolExtent& x : h->pool.ext)
+    if (int rc = nq_aux_fill(h, x.b, x.e); rc != TSB_OK) return rc;
+  h->aux_ok = true;
+  return TSB_OK;
 }
 }  // namespace
+extern "C" {
 
 int tsb_nq_pool_push(tsb_nq* h, const void* nodes, int64_t n) {
   if (!h || n < 0 || (n && !nodes)) return TSB_EINVAL;
@@ -1264,11 +1335,13 @@ int tsb_nq_pool_push(tsb_nq* h, const void* nodes, int64_t n) {
   rc = h->copy_h2d(h->pool.arena[h->pool.cur] + at * sizeof(tsb_nq_node), nodes,
                    static_cast<size_t>(n) * sizeof(tsb_nq_node), h->stream);
   if (rc != TSB_OK) return rc;
+  if (h->pool.size == 0) h->aux_ok = true;  // (nothing else to describe)
   if (h->pool.ext.empty())
     h->pool.ext.push_back({at, at + n});
   else
     h->pool.ext.back().e += n;
   h->pool.size += n;
+  if (h->aux_ok && h->pool.side_rec) return nq_aux_fill(h, at, at + n);  // (ordered after the copy on the handle's stream)
   return TSB_OK;
 }
 
@@ -1297,7 +1370,15 @@ int tsb_nq_pool_step(tsb_nq* h, int m, int M, int64_t* n_parents, uint64_t* n_ch
   const long long top = p.top();
   unsigned long long nc = 0, ns = 0;
   uint8_t* arena = p.arena[p.cur];
-  rc = nq_expand_dispatch(h, arena, pieces, arena + top * sizeof(tsb_nq_node), h->stream, &nc, &ns, /*early=*/true);
+  if (p.side_rec) {  // every node evaluated once, when it is built (nq_expand2.cuh)
+    rc = nq_aux_ensure(h);
+    if (rc != TSB_OK) return rc;
+    unsigned long long* side = reinterpret_cast<unsigned long long*>(p.side[p.cur]);
+    rc = nq_expand_dispatch(h, arena, pieces, arena + top * sizeof(tsb_nq_node), h->stream, &nc, &ns, /*early=*/true, side,
+                            side + top);
+  } else {
+    rc = nq_expand_dispatch(h, arena, pieces, arena + top * sizeof(tsb_nq_node), h->stream, &nc, &ns, /*early=*/true);
+  }
   if (rc != TSB_OK) return rc;
   pool_pop(p, n);
   if (nc) {
@@ -1406,6 +1487,7 @@ int nq_materialize(tsb_nq* h) {
     TSB_CUDA(cudaStreamSynchronize(h->stream));
   }
   h->rounds.in_fat = false;
+  h->aux_ok = false;  // (the exported nodes carry no side words)
   return TSB_OK;
 }
 bool env_no_rounds() {
@@ -1556,6 +1638,7 @@ int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rou
                    1.0 * st.prof[2] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[3] / std::max<unsigned long long>(1, st.rounds),
                    1.0 * st.prof[4] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[5] / std::max<unsigned long long>(1, st.rounds));
     h->rounds.epoch = st.epoch;
+    h->aux_ok = false;
     h->rounds.aux_valid = st.size;
     p.size = st.size;
     p.ext.clear();
@@ -1587,6 +1670,7 @@ int tsb_nq_pool_steal(tsb_nq* victim, tsb_nq* thief, int m, int64_t* n_stolen) {
   rc = pool_steal_front(victim->pool, victim->device, victim->stream, thief->pool, thief->device, thief->stream, m,
                             nq_pool_min_cap(thief), &n);
   *n_stolen = n;
+  if (n) thief->aux_ok = false;  // (the stolen nodes arrive without side words: filled before the thief's next round)
   return rc;
 }
 

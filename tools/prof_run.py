@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A few launches of one kernel family with device-resident inputs, for ncu captures (profiles/README.md):
-python tools/prof_run.py nq | lb1 | lb2 | expand | rounds"""
+python tools/prof_run.py nq | lb1 | lb2 | expand | rounds | pool"""
 import os
 import sys
 
@@ -42,4 +42,7 @@ elif what in ("lb1", "lb2"):
 elif what == "rounds":
     st = tsb200.nqueens_search_device(15, 1, 25, 50000, 1)  # 3 431 rounds in one launch of the persistent kernel
     assert (st.explored_tree, st.explored_sol) == (171129071, 2279184)
+elif what == "pool":
+    st = tsb200.nqueens_search_device(17, 1, 25, 1 << 22, 1)  # 1 922 two-kernel rounds of up to 4 Mi parents
+    assert (st.explored_tree, st.explored_sol) == (8017021931, 95815104)
 print("done", what)
