@@ -50,6 +50,7 @@ struct LlSync {
   unsigned long long slot[2][2 * RND_MAX_CTAS];  // by round parity, one per SUB-slice: epoch << 32 | leaves << 20 | children
   unsigned abort;
 };
+constexpr int LL_MAX_POOLS = 4;  // independent pools one launch can serve (blockIdx.y)
 struct LlParams {
   FatNode* fat;
   long long cap;    // nodes the fat arena holds
@@ -60,6 +61,12 @@ struct LlParams {
   int prof;
   LlSync* sync;
   RoundsState* state;
+};
+// Several INDEPENDENT pools in one cooperative launch: grid (G, pools), the CTAs of row y run the rounds of pool y and
+// never look at another row.  A round of one pool is a chain of L2 round trips (count exchange, store -> poll) with
+// ~1 us of work in between; two co-resident CTAs per SM working on different pools fill each other's waits.
+struct LlMultiParams {
+  LlParams pool[LL_MAX_POOLS];
 };
 
 // ---- CTA barriers on a named barrier (kept from the version that had a side warp outside them)
@@ -187,7 +194,8 @@ __device__ __forceinline__ void ll_build_child(const uint32_t (*parent)[8], int 
 }
 
 template <int N, int T>
-__global__ void __launch_bounds__(T, 1) nq_rounds_ll_kernel(const __grid_constant__ LlParams prm) {
+__global__ void __launch_bounds__(T, 2) nq_rounds_ll_kernel(const __grid_constant__ LlMultiParams mprm) {
+  const LlParams& prm = mprm.pool[blockIdx.y];
   extern __shared__ __align__(128) uint8_t smem_raw[];
   LlSmem<T>& sm = *reinterpret_cast<LlSmem<T>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;

@@ -552,6 +552,7 @@ struct RoundsCtx {
 };
 
 struct tsb_nq : Base {
+  tsb_nq* sibling = nullptr;  // a second pool on the same device, owned by this handle (tsb_nq_sibling)
   bool aux_ok = false;  // every node of the pool has its side word (nq_expand2.cuh)
   int N = 0, g = 1;
   RoundsCtx rounds;
@@ -1205,6 +1206,8 @@ int tsb_nq_create(tsb_nq** out, int device, int N, int g, int M_max) {
 
 void tsb_nq_destroy(tsb_nq* h) {
   if (!h) return;
+  if (h->sibling) tsb_nq_destroy(h->sibling);
+  h->sibling = nullptr;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->ex.release();
@@ -1426,15 +1429,16 @@ int nq_rounds_launch(tsb_nq* h, const tsb::RoundsParams& prm, int grid, cudaStre
   return TSB_EINVAL;
 }
 template <int N>
-int nq_ll_launch_n(tsb_nq* h, const tsb::LlParams& prm, int grid, cudaStream_t s) {
+int nq_ll_launch_n(tsb_nq* h, const tsb::LlMultiParams& prm, int grid, int pools, cudaStream_t s) {
   auto kernel = tsb::nq_rounds_ll_kernel<N, tsb::LL_T>;
   const size_t smem = sizeof(tsb::LlSmem<tsb::LL_T>) + 128;
   if (!h->rounds.attr_ll) {
     TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     h->rounds.attr_ll = true;
   }
-  void* args[] = {const_cast<tsb::LlParams*>(&prm)};
-  TSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid), dim3(tsb::LL_T), args, smem, s));
+  void* args[] = {const_cast<tsb::LlMultiParams*>(&prm)};
+  // cooperative: all CTAs of all pools co-resident (two per SM when there are two pools), or the launch fails
+  TSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid, pools), dim3(tsb::LL_T), args, smem, s));
   h->launches++;
   return TSB_OK;
 }
@@ -1448,11 +1452,11 @@ int nq_ll_import_n(tsb_nq* h, long long size, cudaStream_t s) {
   }
   return TSB_OK;
 }
-int nq_ll_launch(tsb_nq* h, const tsb::LlParams& prm, int grid, cudaStream_t s) {
+int nq_ll_launch(tsb_nq* h, const tsb::LlMultiParams& prm, int grid, int pools, cudaStream_t s) {
   switch (h->N) {
 #define TSB_NQ_CASE(n) \
   case n:              \
-    return nq_ll_launch_n<n>(h, prm, grid, s);
+    return nq_ll_launch_n<n>(h, prm, grid, pools, s);
     TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
     TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
     TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
@@ -1494,6 +1498,114 @@ bool env_no_rounds() {
   const char* v = std::getenv("TSB200_NO_ROUNDS");
   return v && *v && *v != '0';
 }
+// grid (CTAs per pool) of the persistent kernel for chunks of up to M parents; 0: M is too large for it
+int nq_ll_grid(const tsb_nq* h, int M) {
+  int grid = std::min(h->di.sms, static_cast<int>(tsb::RND_MAX_CTAS));
+  grid = h->rounds.ctas > 0 ? std::min(grid, h->rounds.ctas) : std::max(1, (grid * 7 / 8) & ~1);  // measured best at 128 of 148 SMs
+  while (static_cast<long long>(grid) * tsb::LL_SLICE < M && grid < h->di.sms) ++grid;  // (M decides)
+  if (static_cast<long long>(M) > static_cast<long long>(grid) * tsb::LL_SLICE || !h->di.coop || env_no_rounds()) return 0;
+  return grid;
+}
+// Up to `max_rounds` rounds of EACH of the K pools (handles on one device, same N) in launches of the persistent
+// kernel that serve all pools that still have work: grid (grid, pools).  out[4 i ..] += {rounds, parents, children,
+// solutions} of pool i.  A pool leaves the launch on its own (done, round budget, arena full, layer table full); the
+// launch ends when every pool has left, the pools that stopped for room grow and go again.
+int nq_ll_run_multi(tsb_nq* const* hs, int K, int m, int M, int grid, int64_t max_rounds, uint64_t* out) {
+  int64_t left[tsb::LL_MAX_POOLS];
+  bool active[tsb::LL_MAX_POOLS];
+  for (int i = 0; i < K; i++) {
+    left[i] = max_rounds;
+    active[i] = true;
+    nq_pool_setup(hs[i]);
+    int rc = hs[i]->rounds.ensure(hs[i]->stream);
+    if (rc != TSB_OK) return rc;
+  }
+  const bool prof = std::getenv("TSB200_ROUNDS_PROF") != nullptr;
+  for (;;) {
+    tsb::LlMultiParams mp;
+    std::memset(&mp, 0, sizeof(mp));
+    int map[tsb::LL_MAX_POOLS], n_act = 0;
+    long long need_of[tsb::LL_MAX_POOLS];
+    for (int i = 0; i < K; i++) {
+      tsb_nq* h = hs[i];
+      DevicePool& p = h->pool;
+      if (!active[i] || p.size < m || left[i] <= 0) {
+        active[i] = false;
+        continue;
+      }
+      const long long n = std::min<long long>(p.size, M);
+      const long long need = p.size - n + n * h->N;
+      int rc = TSB_OK;
+      if (h->rounds.in_fat && need > p.cap) rc = nq_materialize(h);  // (grows below and imports again)
+      if (rc != TSB_OK) return rc;
+      if (!h->rounds.in_fat) {
+        // the plain pool as ONE contiguous stack [0, size) with room for the worst case of the next round
+        if (need > p.cap)
+          rc = p.compact(h->stream, std::max<long long>(2 * p.cap, need + need / 2));
+        else if (p.ext.size() != 1 || p.ext[0].b != 0)
+          rc = p.compact(h->stream, p.cap);
+        if (rc == TSB_OK) rc = h->rounds.ensure_fat(p.cap, h->stream);
+        if (rc == TSB_OK) rc = nq_ll_import(h, p.size, h->stream);
+        if (rc != TSB_OK) return rc;
+        h->rounds.in_fat = true;
+        if (n_act > 0) TSB_CUDA(cudaStreamSynchronize(h->stream));  // (the launch goes on the first pool's stream)
+      }
+      tsb::LlParams& prm = mp.pool[n_act];
+      prm.fat = h->rounds.d_fat;
+      prm.cap = std::min(p.cap, h->rounds.fat_cap);
+      prm.size0 = p.size;
+      prm.epoch0 = h->rounds.epoch;
+      prm.m = m;
+      prm.M = M;
+      prm.max_rounds = left[i];
+      prm.prof = prof;
+      prm.sync = h->rounds.d_ll;
+      prm.state = h->rounds.d_state;
+      h->rounds.h_state->exit_code = -1;
+      need_of[n_act] = need;
+      map[n_act++] = i;
+    }
+    if (n_act == 0) break;
+    tsb_nq* h0 = hs[map[0]];
+    int rc = nq_ll_launch(h0, mp, grid, n_act, h0->stream);
+    if (rc != TSB_OK) return rc;
+    TSB_CUDA(cudaStreamSynchronize(h0->stream));
+    for (int a = 0; a < n_act; a++) {
+      const int i = map[a];
+      tsb_nq* h = hs[i];
+      DevicePool& p = h->pool;
+      const tsb::RoundsState st = *h->rounds.h_state;
+      if (st.exit_code < 0 || st.exit_code == tsb::RND_EXIT_ABORT) {
+        g_last_cuda_error = "nq_rounds_ll_kernel: watchdog abort (a flag exchange or a node poll did not complete)";
+        return TSB_ECUDA;
+      }
+      if (prof)
+        std::fprintf(stderr, "[tsb200] LL rounds kernel (pool %d of %d): %llu rounds; CTA 0 cycles per round: build %.0f | fence-check %.0f "
+                     "poll-nodes %.0f scan+items %.0f gather-wait %.0f store %.0f signal %.0f\n", a, n_act,
+                     static_cast<unsigned long long>(st.rounds), 1.0 * st.prof[6] / std::max<unsigned long long>(1, st.rounds),
+                     1.0 * st.prof[0] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[1] / std::max<unsigned long long>(1, st.rounds),
+                     1.0 * st.prof[2] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[3] / std::max<unsigned long long>(1, st.rounds),
+                     1.0 * st.prof[4] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[5] / std::max<unsigned long long>(1, st.rounds));
+      h->rounds.epoch = st.epoch;
+      p.size = st.size;
+      p.ext.clear();
+      if (p.size) p.ext.push_back({0, p.size});
+      out[4 * i + 0] += st.rounds;
+      out[4 * i + 1] += st.parents;
+      out[4 * i + 2] += st.children;
+      out[4 * i + 3] += st.solutions;
+      left[i] -= static_cast<int64_t>(st.rounds);
+      if (st.exit_code == tsb::RND_EXIT_SPACE) {
+        if (st.rounds == 0 && need_of[a] <= p.cap) return TSB_ENOMEM;  // (cannot happen)
+        rc = nq_materialize(h);  // back to the plain arena, which then grows
+        if (rc != TSB_OK) return rc;
+      } else if (st.exit_code != tsb::RND_EXIT_RELAUNCH) {  // (layer table full: a fresh launch trusts the whole pool)
+        active[i] = false;                                    // DONE or PAUSE
+      }
+    }
+  }
+  return TSB_OK;
+}
 }  // namespace
 extern "C" {
 
@@ -1531,69 +1643,14 @@ int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rou
   nq_pool_setup(h);
   if (h->rounds.version == 3 && static_cast<long long>(M) <= static_cast<long long>(grid) * tsb::LL_SLICE) {
     // ---- the fence-free kernel on the fat arena (nq_rounds_ll.cuh)
-    while (p.size >= m && static_cast<int64_t>(*n_rounds) < max_rounds) {
-      const long long n = std::min<long long>(p.size, M);
-      const long long need = p.size - n + n * h->N;
-      if (!h->rounds.in_fat) {
-        // the plain pool as ONE contiguous stack [0, size) with room for the worst case of the next round
-        if (need > p.cap)
-          rc = p.compact(h->stream, std::max<long long>(2 * p.cap, need + need / 2));
-        else if (p.ext.size() != 1 || p.ext[0].b != 0)
-          rc = p.compact(h->stream, p.cap);
-        if (rc == TSB_OK) rc = h->rounds.ensure_fat(p.cap, h->stream);
-        if (rc == TSB_OK) rc = nq_ll_import(h, p.size, h->stream);
-        if (rc != TSB_OK) return rc;
-        h->rounds.in_fat = true;
-      } else if (need > p.cap) {
-        rc = nq_materialize(h);
-        if (rc != TSB_OK) return rc;
-        continue;  // (grows and imports again)
-      }
-      tsb::LlParams prm;
-      prm.fat = h->rounds.d_fat;
-      prm.cap = std::min(p.cap, h->rounds.fat_cap);
-      prm.size0 = p.size;
-      prm.epoch0 = h->rounds.epoch;
-      prm.m = m;
-      prm.M = M;
-      prm.max_rounds = max_rounds - static_cast<int64_t>(*n_rounds);
-      prm.prof = std::getenv("TSB200_ROUNDS_PROF") != nullptr;
-      prm.sync = h->rounds.d_ll;
-      prm.state = h->rounds.d_state;
-      h->rounds.h_state->exit_code = -1;
-      rc = nq_ll_launch(h, prm, grid, h->stream);
-      if (rc != TSB_OK) return rc;
-      TSB_CUDA(cudaStreamSynchronize(h->stream));
-      const tsb::RoundsState st = *h->rounds.h_state;
-      if (st.exit_code < 0 || st.exit_code == tsb::RND_EXIT_ABORT) {
-        g_last_cuda_error = "nq_rounds_ll_kernel: watchdog abort (a flag exchange or a node poll did not complete)";
-        return TSB_ECUDA;
-      }
-      if (prm.prof)
-        std::fprintf(stderr, "[tsb200] LL rounds kernel: %llu rounds; CTA 0 cycles per round: build %.0f | fence-check %.0f poll-nodes %.0f "
-                     "scan+items %.0f gather-wait %.0f store %.0f signal %.0f\n", static_cast<unsigned long long>(st.rounds),
-                     1.0 * st.prof[6] / std::max<unsigned long long>(1, st.rounds),
-                     1.0 * st.prof[0] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[1] / std::max<unsigned long long>(1, st.rounds),
-                     1.0 * st.prof[2] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[3] / std::max<unsigned long long>(1, st.rounds),
-                     1.0 * st.prof[4] / std::max<unsigned long long>(1, st.rounds), 1.0 * st.prof[5] / std::max<unsigned long long>(1, st.rounds));
-      h->rounds.epoch = st.epoch;
-      p.size = st.size;
-      p.ext.clear();
-      if (p.size) p.ext.push_back({0, p.size});
-      *n_rounds += st.rounds;
-      *n_parents += st.parents;
-      *n_children += st.children;
-      *n_solutions += st.solutions;
-      if (st.exit_code == tsb::RND_EXIT_SPACE) {
-        if (st.rounds == 0 && need <= p.cap) return TSB_ENOMEM;  // (cannot happen)
-        rc = nq_materialize(h);  // back to the plain arena, which then grows
-        if (rc != TSB_OK) return rc;
-        continue;
-      }
-      if (st.exit_code == tsb::RND_EXIT_RELAUNCH) continue;  // (layer table full: a fresh launch trusts the whole pool)
-      break;  // DONE or PAUSE
-    }
-    return TSB_OK;
+    uint64_t out[4] = {0, 0, 0, 0};
+    tsb_nq* one[1] = {h};
+    rc = nq_ll_run_multi(one, 1, m, M, grid, max_rounds, out);
+    *n_rounds = out[0];
+    *n_parents = out[1];
+    *n_children = out[2];
+    *n_solutions = out[3];
+    return rc;
   }
   nq_pool_setup(h);
   while (p.size >= m && static_cast<int64_t>(*n_rounds) < max_rounds) {
@@ -1651,6 +1708,44 @@ int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rou
     if (st.exit_code != tsb::RND_EXIT_SPACE) break;  // DONE or PAUSE
   }
   return TSB_OK;
+}
+
+int tsb_nq_sibling(tsb_nq* h, tsb_nq** sibling) {
+  if (!h || !sibling) return TSB_EINVAL;
+  if (!h->sibling) {
+    int rc = tsb_nq_create(&h->sibling, h->device, h->N, h->g, h->M_max);
+    if (rc != TSB_OK) return rc;
+  }
+  *sibling = h->sibling;
+  return TSB_OK;
+}
+
+int tsb_nq_pools_per_launch(const tsb_nq* h, int M) {
+  if (!h || M < 1 || M > h->M_max || h->rounds.version != 3) return 1;
+  const int grid = nq_ll_grid(h, M);
+  return grid > 0 && grid <= h->di.sms ? 2 : 1;  // (two co-resident CTAs per SM, one of each pool)
+}
+
+int tsb_nq_pool_run_multi(tsb_nq* const* handles, int n_pools, int m, int M, int64_t max_rounds, uint64_t* out) {
+  if (!handles || n_pools < 1 || n_pools > tsb::LL_MAX_POOLS || m < 1 || M < 1 || max_rounds < 0 || !out) return TSB_EINVAL;
+  for (int i = 0; i < n_pools; i++) {
+    const tsb_nq* h = handles[i];
+    if (!h || M > h->M_max || h->device != handles[0]->device || h->N != handles[0]->N) return TSB_EINVAL;
+    for (int j = 0; j < i; j++)
+      if (handles[j] == h) return TSB_EINVAL;
+  }
+  std::memset(out, 0, sizeof(uint64_t) * 4 * n_pools);
+  TSB_CUDA(cudaSetDevice(handles[0]->device));
+  const int grid = handles[0]->rounds.version == 3 ? nq_ll_grid(handles[0], M) : 0;
+  // two pools need two co-resident CTAs per SM; chunks too large for the persistent kernel: one pool after the other
+  if (grid == 0 || (n_pools > 1 && static_cast<long long>(grid) * n_pools > 2LL * handles[0]->di.sms)) {
+    for (int i = 0; i < n_pools; i++) {
+      int rc = tsb_nq_pool_run(handles[i], m, M, max_rounds, &out[4 * i], &out[4 * i + 1], &out[4 * i + 2], &out[4 * i + 3]);
+      if (rc != TSB_OK) return rc;
+    }
+    return TSB_OK;
+  }
+  return nq_ll_run_multi(handles, n_pools, m, M, grid, max_rounds, out);
 }
 
 int tsb_nq_pool_steal(tsb_nq* victim, tsb_nq* thief, int m, int64_t* n_stolen) {
@@ -1767,7 +1862,9 @@ int tsb_nq_set_xfer(tsb_nq* h, int mode) {
   h->xfer = mode;
   return TSB_OK;
 }
-uint64_t tsb_nq_kernel_launches(const tsb_nq* h) { return h ? h->launches : 0; }
+uint64_t tsb_nq_kernel_launches(const tsb_nq* h) {
+  return h ? h->launches + (h->sibling ? h->sibling->launches : 0) : 0;
+}
 void* tsb_nq_stream(const tsb_nq* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
 
 // ---------------------------------------------------------------- PFSP

@@ -284,6 +284,9 @@ inline void board_abort(StealBoard* sb, int me) {
   sb->cv.notify_all();
 }
 
+template <class Node>
+void static_split(Pool<Node>& pool, int D, std::vector<Pool<Node>>& multi);
+
 // rounds per library call when other tasks may want to steal (a victim serves requests between calls)
 inline int64_t rounds_per_call(const StealBoard* sb, int M) { return !sb ? INT64_MAX : M <= 75776 ? 256 : 4; }
 
@@ -310,10 +313,79 @@ void nq_devpool_rounds(tsb_nq* h, int m, int M, StealBoard* sb, int me, GpuTaskR
   }
   if (r.rc != TSB_OK) board_abort(sb, me);
 }
+// Two pools per task (TSB200_POOLS=1 turns it off): for chunks that fit the persistent kernel a round is a chain of
+// L2 round trips with ~1 us of work in between, so the task's share of the warm-up pool is split once more — the
+// reference's own strided split (static_split) — into two device pools whose rounds run in ONE launch
+// (tsb_nq_pool_run_multi), a CTA of each on every SM filling the other's waits.  Each pool follows the reference's
+// rule on its own nodes: for D tasks the chunk sequence is that of a 2-level split into 2 D pools, the totals are
+// split-invariant.  When one pool of the pair runs dry it takes the oldest half of the other (as between tasks).
+inline int nq_pools_wanted(int M) {  // (decides the warm-up size, before any handle exists)
+  const char* v = std::getenv("TSB200_POOLS");
+  if (v && std::atoi(v) == 1) return 1;
+  return M <= 65536 ? 2 : 1;  // 512 parents x 128 CTAs: the persistent kernel's range
+}
+inline bool nq_pair_mode(tsb_nq* h, int M) { return nq_pools_wanted(M) == 2 && tsb_nq_pools_per_launch(h, M) >= 2; }
+void nq_devpool_pair_rounds(tsb_nq* h, tsb_nq* sib, int m, int M, StealBoard* sb, int me, GpuTaskResult& r) {
+  const bool no_steal = [] {
+    const char* v = std::getenv("TSB200_NO_STEAL");
+    return v && *v && *v != '0';
+  }();
+  tsb_nq* pair[2] = {h, sib};
+  // a thief task is served from the fuller pool of the pair
+  const auto steal = [&](void*, void* t, int64_t* got) {
+    tsb_nq* v = tsb_nq_pool_size(h) >= tsb_nq_pool_size(sib) ? h : sib;
+    return tsb_nq_pool_steal(v, static_cast<tsb_nq*>(t), m, got);
+  };
+  const long long floor_ = steal_floor(m, M);
+  while (r.rc == TSB_OK) {
+    long long a = tsb_nq_pool_size(h), b = tsb_nq_pool_size(sib);
+    if (!no_steal && ((a < m && b >= floor_) || (b < m && a >= floor_))) {  // balance inside the pair
+      int64_t got = 0;
+      r.rc = a < m ? tsb_nq_pool_steal(sib, h, m, &got) : tsb_nq_pool_steal(h, sib, m, &got);
+      if (r.rc != TSB_OK) break;
+      a = tsb_nq_pool_size(h);
+      b = tsb_nq_pool_size(sib);
+    }
+    if (a < m && b < m) {
+      if (!board_acquire(sb, me, a + b, floor_)) break;
+      continue;
+    }
+    uint64_t out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    r.rc = tsb_nq_pool_run_multi(pair, 2, m, M, sb ? rounds_per_call(sb, M) : 2048, out);
+    if (r.rc != TSB_OK) break;
+    for (int i = 0; i < 2; i++) {
+      r.offloads += out[4 * i];
+      r.parents += out[4 * i + 1];
+      r.tree += out[4 * i + 2];
+      r.sol += out[4 * i + 3];
+    }
+    r.rc = board_service(sb, me, std::max(tsb_nq_pool_size(h), tsb_nq_pool_size(sib)), floor_, steal);
+  }
+  if (r.rc != TSB_OK) board_abort(sb, me);
+}
 // pool -> device, all rounds, leftovers (fewer than m nodes) back to the host pool for step 3
 void nq_devpool_on(tsb_nq* h, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResult& r, StealBoard* sb = nullptr,
                    int me = 0) {
   const uint64_t l0 = tsb_nq_kernel_launches(h);
+  tsb_nq* sib = nullptr;
+  if (nq_pair_mode(h, M) && tsb_nq_sibling(h, &sib) == TSB_OK && sib) {
+    std::vector<Pool<tsb_nq_node>> half;
+    static_split(pool, 2, half);
+    r.rc = tsb_nq_pool_push(h, &half[0].el[half[0].front], static_cast<int64_t>(half[0].size));
+    if (r.rc == TSB_OK) r.rc = tsb_nq_pool_push(sib, &half[1].el[half[1].front], static_cast<int64_t>(half[1].size));
+    if (sb) sb->publish_handle(me, r.rc == TSB_OK ? h : nullptr, std::max(tsb_nq_pool_size(h), tsb_nq_pool_size(sib)));
+    if (r.rc == TSB_OK) nq_devpool_pair_rounds(h, sib, m, M, sb, me, r);
+    for (tsb_nq* x : {h, sib}) {
+      if (r.rc != TSB_OK) break;
+      const int64_t left = tsb_nq_pool_size(x);
+      std::vector<tsb_nq_node> rest(static_cast<size_t>(left) + 1);
+      int64_t n = 0;
+      r.rc = tsb_nq_pool_drain(x, rest.data(), left, &n);
+      for (int64_t i = 0; i < n && r.rc == TSB_OK; i++) pool.pushBack(rest[i]);
+    }
+    r.launches = tsb_nq_kernel_launches(h) - l0;
+    return;
+  }
   r.rc = tsb_nq_pool_push(h, &pool.el[pool.front], static_cast<int64_t>(pool.size));
   pool.front = 0;
   pool.size = 0;
@@ -760,7 +832,8 @@ static int nq_search_device_impl(int N, int g, int m, int M, int D, int part, in
   uint64_t tree = 0, sol = 0;
   tsb_nq_node parent;
   double t0 = now_s();
-  while (pool.size < static_cast<size_t>(D) * m) {  // step 1 on the CPU, as in the reference
+  // step 1 on the CPU, as in the reference: m nodes for every pool (two per task in pair mode, see nq_pair_mode)
+  while (pool.size < static_cast<size_t>(D) * m * nq_pools_wanted(M)) {
     if (!pool.popFront(parent)) break;
     nq_decompose(N, parent, tree, sol, pool);
   }

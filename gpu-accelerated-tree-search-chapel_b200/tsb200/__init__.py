@@ -14,11 +14,11 @@ device every call raises.
 from ._lib import (LB1, LB1_D, LB2, XFER_AUTO, XFER_MEMCPY, XFER_ZEROCOPY, PfspTables, SearchStats, TsbError,
                    check, lib)
 from .nqueens import (NQ_NODE_DTYPE, NQueensEvaluator, nqueens_search, nqueens_search_device,
-                      nqueens_search_device_part, nqueens_warmup)
+                      nqueens_pool_run_multi, nqueens_search_device_part, nqueens_warmup)
 from .pfsp import (PFSP_NODE_DTYPE, PFSP_NODE50_DTYPE, LB_NAMES, LB2_VARIANTS, PfspEvaluator, taillard_tables50, pfsp_search, pfsp_search_device,
                    pfsp_search_device_part, taillard_tables)
 
-__all__ = ["NQueensEvaluator", "PfspEvaluator", "nqueens_warmup", "nqueens_search", "nqueens_search_device", "nqueens_search_device_part", "pfsp_search", "pfsp_search_device",
+__all__ = ["NQueensEvaluator", "PfspEvaluator", "nqueens_warmup", "nqueens_pool_run_multi", "nqueens_search", "nqueens_search_device", "nqueens_search_device_part", "pfsp_search", "pfsp_search_device",
            "pfsp_search_device_part",
            "taillard_tables",
            "NQ_NODE_DTYPE", "PFSP_NODE_DTYPE", "PFSP_NODE50_DTYPE", "LB2_VARIANTS", "taillard_tables50", "LB_NAMES", "LB1", "LB1_D", "LB2", "TsbError", "lib", "check",

@@ -132,6 +132,16 @@ class NQueensEvaluator:
         check(lib().tsb_nq_evaluate_device(self._h, parents_ptr, count, labels_ptr, stream), "tsb_nq_evaluate_device")
 
 
+def nqueens_pool_run_multi(evaluators, m: int, M: int, max_rounds: int = 2**62):
+    """up to max_rounds rounds of each evaluator's device pool in shared launches of the persistent kernel
+    (tsb_nq_pool_run_multi): [(rounds, parents, children, solutions)] per pool"""
+    K = len(evaluators)
+    hs = (C.c_void_p * K)(*[ev._h for ev in evaluators])
+    out = (C.c_uint64 * (4 * K))()
+    check(lib().tsb_nq_pool_run_multi(hs, K, m, M, max_rounds, out), "tsb_nq_pool_run_multi")
+    return [tuple(int(out[4 * i + j]) for j in range(4)) for i in range(K)]
+
+
 def nqueens_warmup(N: int, min_size: int = 25):
     """step 1 of the drivers (nqueens_gpu_chpl.chpl:169-175): (pool nodes, explored tree, solutions)"""
     cap = max(1024, 32 * min_size)

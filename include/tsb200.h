@@ -151,6 +151,21 @@ int tsb_nq_pool_steal(tsb_nq* victim, tsb_nq* thief, int m, int64_t* n_stolen);
 int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rounds, uint64_t* n_parents,
                     uint64_t* n_children, uint64_t* n_solutions);
 
+/* The same for up to 4 INDEPENDENT pools (handles on one device, same N) served by ONE launch of the persistent
+ * kernel: the CTAs of pool i run pool i's rounds and never look at another pool; with two pools every SM hosts one CTA
+ * of each and the L2 round trips that order one pool's rounds (count exchange, store -> poll) are filled with the
+ * other pool's work.  Each pool follows, on its own nodes, exactly the sequence tsb_nq_pool_run produces — this is the
+ * reference's multi-GPU static split (nqueens_multigpu_chpl.chpl:200-224: D tasks, D pools) with several of the D
+ * pools living on one GPU.  out[4 i .. 4 i + 3] = {rounds, parents, children, solutions} of pool i.  Chunks too large
+ * for the persistent kernel: the pools are run one after the other. */
+int tsb_nq_pool_run_multi(tsb_nq* const* handles, int n_pools, int m, int M, int64_t max_rounds, uint64_t* out);
+/* A second, independent pool on the same device, created on first use and owned by `h` (destroyed with it; its
+ * launches are included in h's tsb_nq_kernel_launches count): what a driver pairs with `h` in tsb_nq_pool_run_multi. */
+int tsb_nq_sibling(tsb_nq* h, tsb_nq** sibling);
+/* How many pools one launch of the persistent kernel can serve for chunks of up to M parents on h's device: 2 when
+ * M fits the persistent kernel (two co-resident CTAs per SM), else 1. */
+int tsb_nq_pools_per_launch(const tsb_nq* h, int M);
+
 /* page-lock + map a caller-owned host array for the lifetime of the handle (see the header comment);
  * TSB_EINVAL if the range partly overlaps a registered one / was not registered */
 int tsb_nq_register_host(tsb_nq* h, void* ptr, size_t bytes);

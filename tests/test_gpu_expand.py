@@ -76,6 +76,7 @@ def test_device_pool_compaction_and_growth(golden_dir, monkeypatch):
     """a tiny arena (TSB200_POOL_CAP) forces the extent stack to be compacted into the second arena and the
     arenas to grow many times during a search; counts and chunk sequence must not change"""
     monkeypatch.setenv("TSB200_POOL_CAP", "3000")
+    monkeypatch.setenv("TSB200_POOLS", "1")  # one pool per task: the reference's D = 1 chunk sequence
     N, m, M = 12, 25, 500
     counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
     st = tsb200.nqueens_search_device(N, 1, m, M)
@@ -88,6 +89,7 @@ def test_device_pool_compaction_and_growth(golden_dir, monkeypatch):
                                      (14, 25, 50000, 1), (15, 25, 1 << 20, 1), (13, 25, 2000, 3), (14, 25, 50000, 4)])
 def test_device_resident_search_counts(golden_dir, N, m, M, D, monkeypatch):
     monkeypatch.setenv("TSB200_NO_STEAL", "1")  # the static split alone: the reference driver's chunk sequence
+    monkeypatch.setenv("TSB200_POOLS", "1")     # ... with one pool per task
     counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
     st = tsb200.nqueens_search_device(N, 1, m, M, D)
     assert (st.explored_tree, st.explored_sol) == (counts["tree"], counts["sol"])
@@ -97,6 +99,60 @@ def test_device_resident_search_counts(golden_dir, N, m, M, D, monkeypatch):
         assert 0 < st.kernel_launches < max(16, st.offloads // 4 + 16)
     else:
         assert st.kernel_launches == 2 * st.offloads  # count, build
+
+
+@pytest.mark.parametrize("N,m,M", [(10, 25, 50000), (12, 5, 300), (13, 25, 4096), (14, 25, 50000), (15, 25, 50000)])
+def test_two_pools_per_task_is_the_reference_split_into_two_tasks(golden_dir, N, m, M, monkeypatch):
+    """default for chunks that fit the persistent kernel: the task's pool is split once more (the reference's strided
+    split) into two device pools whose rounds share one launch (tsb_nq_pool_run_multi).  Without stealing, D = 1 is
+    then exactly the reference's D = 2 run: same warm-up, same split, same chunk sequence in each pool"""
+    monkeypatch.setenv("TSB200_NO_STEAL", "1")
+    monkeypatch.delenv("TSB200_POOLS", raising=False)
+    counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
+    st = tsb200.nqueens_search_device(N, 1, m, M, 1)
+    assert (st.explored_tree, st.explored_sol) == (counts["tree"], counts["sol"])
+    ref = po.nq_search_offload(N, 1, m, M, 2)
+    assert (st.offloads, st.offloaded_parents) == (ref.offloads, ref.offloaded_parents)
+    assert 0 < st.kernel_launches < max(24, st.offloads // 4 + 24)
+
+
+@pytest.mark.parametrize("N,m,M,D", [(13, 25, 2000, 1), (15, 25, 50000, 1), (14, 25, 50000, 3), (15, 25, 30000, 8)])
+def test_two_pools_per_task_with_stealing_totals(golden_dir, N, m, M, D, monkeypatch):
+    monkeypatch.delenv("TSB200_POOLS", raising=False)
+    monkeypatch.delenv("TSB200_NO_STEAL", raising=False)
+    counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
+    st = tsb200.nqueens_search_device(N, 1, m, M, D)
+    assert (st.explored_tree, st.explored_sol) == (counts["tree"], counts["sol"])
+
+
+@pytest.mark.parametrize("N,m,M,K", [(12, 25, 700, 2), (14, 25, 50000, 2), (13, 5, 3000, 3), (11, 25, 700, 4), (15, 25, 1 << 17, 2)])
+def test_pool_run_multi_equals_separate_pool_runs(N, m, M, K):
+    """K pools in shared launches of the persistent kernel against each pool run on its own: same counters, byte-
+    identical leftovers (K > 2 or chunks beyond the persistent kernel: served one after the other by the library)"""
+    rng = np.random.default_rng(N * 77 + K)
+    starts = [rand_nq(rng, N, 40 + 13 * i, depth_lo=1, depth_hi=2) for i in range(K)]
+    multi = [tsb200.NQueensEvaluator(N, M=M) for _ in range(K)]
+    try:
+        for ev, st in zip(multi, starts):
+            ev.pool_push(st)
+        got = tsb200.nqueens_pool_run_multi(multi, m, M, 10 ** 9)
+        for i, st in enumerate(starts):
+            with tsb200.NQueensEvaluator(N, M=M) as one:
+                one.pool_push(st)
+                want = one.pool_run(m, M, 10 ** 9)
+                assert got[i] == want
+                assert multi[i].pool_size == one.pool_size
+                assert multi[i].pool_drain().tobytes() == one.pool_drain().tobytes()
+        # a bounded number of rounds per pool
+        for ev, st in zip(multi, starts):
+            ev.pool_push(st)
+        part = tsb200.nqueens_pool_run_multi(multi, m, M, 3)
+        assert all(x[0] <= 3 for x in part)
+        rest = tsb200.nqueens_pool_run_multi(multi, m, M, 10 ** 9)
+        assert [tuple(a + b for a, b in zip(x, y)) for x, y in zip(part, rest)] == got
+    finally:
+        for ev in multi:
+            ev.close()
 
 
 def test_side_word_variant_of_the_round_kernels_counts():
@@ -109,7 +165,7 @@ def test_side_word_variant_of_the_round_kernels_counts():
             "print(st.explored_tree, st.explored_sol, st.offloads, st.kernel_launches)") % (
                 os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                 os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpu-accelerated-tree-search-chapel_b200"))
-    env = dict(os.environ, TSB200_AUX="1", TSB200_NO_STEAL="1")
+    env = dict(os.environ, TSB200_AUX="1", TSB200_NO_STEAL="1", TSB200_POOLS="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     tree, sol, offloads, launches = map(int, out.stdout.split())
