@@ -6,14 +6,15 @@ g=1 m=25 --M 50000.  A *step* is one whole search; Mnodes/s = explored tree / ti
 prints (nqueens_gpu_chpl.chpl:39-46).  Every step the explored tree and the solution count are checked against
 the reference's (8 017 021 931 / 95 815 104).
   value : step 2 (the offload loop, nqueens_gpu_chpl.chpl:197-215) with the warm-up pool already resident in HBM
-          on a pre-created handle — tsb_nq_pool_run, CUDA events on the handle's stream around it;
-          children produced / event time
+          on pre-created handles — what the search driver does: the pool split (the reference's strided split) into
+          four device pools, tsb_nq_pool_run_multi until all are dry (a dry pool takes half of the fullest), CUDA
+          events around it; children produced / event time
   e2e   : the whole search through the reference-facing C-ABI call with host inputs and outputs
           (tsb_nq_search_on: step 1 on the CPU, the warm-up pool copied host->device, all rounds, the leftover
           nodes and the counters copied device->host, step 3 on the CPU), wall clock; explored tree / time
-  roofline : nq_rounds_kernel, the one kernel of that timed region: 21 B read per parent + 21 B written per child
-          (= 42 B per explored node) / event time.  At --M 50000 a round moves ~2 MB and is bound by the two flag
-          exchanges that order it after the previous round, not by HBM; the bandwidth-bound kernels are listed
+  roofline : nq_rounds_ll_kernel, the one kernel of that timed region: 21 B read per parent + 21 B written per child
+          (= 42 B per explored node) / event time.  At --M 50000 a round moves ~2 MB and is bound by the L2 round
+          trips that order it after the previous round, not by HBM; the bandwidth-bound kernels are listed
           under "kernels" with their own fractions
   N > 1 (torchrun) : the same search split over N GPUs (static split of the warm-up pool + stealing between the
           device pools over NVLink), driven by rank 0 in one process with one host thread per GPU, as the
@@ -264,8 +265,12 @@ def make_config(gpus, M=M_HEAD):
     return {"workload": f"N-Queens N={N_HEAD} g=1 m={m_HEAD} --M {M}: whole search, Mnodes/s = explored tree / time "
                         "(BASELINE configs[1]; the reference's default chunk size)",
             "N": N_HEAD, "g": 1, "m": m_HEAD, "M": M,
-            "parallelism": f"{gpus} GPU(s): static split of the warm-up pool, one device pool per GPU, stealing "
-                           "between device pools",
+            "parallelism": f"{gpus} GPU(s): static split of the warm-up pool over the GPUs (one task per GPU, as the "
+                           "reference's --D) and, on each GPU, once more into 4 device pools whose rounds (chunks of "
+                           "<= M parents each, popBackBulk(m, M) per pool) share every launch of the persistent kernel; "
+                           "stealing between device pools.  TSB200_POOLS=1: one pool per GPU (the reference's D = 1 "
+                           "chunk sequence, 0.74 s per search instead of 0.41 s)",
+            "pools_per_gpu": 4,
             "l2": "every step streams its whole pool through HBM (8.0 G nodes x 42 B >> the 126 MB L2); no buffer "
                   "is reused between steps"}
 
@@ -312,7 +317,33 @@ def run_headline_1gpu(steps, warmup, device_index, M=M_HEAD, N=N_HEAD):
     t_c0 = time.perf_counter()
     ev = tsb200.NQueensEvaluator(N, 1, M, device=device_index)
     t_create = time.perf_counter() - t_c0
-    warm, wtree, wsol = tsb200.nqueens_warmup(N, m_HEAD)
+    # pools per GPU: what the search driver uses (tsb_host.cpp nq_pools_of): the task's warm-up pool is split once more
+    # (the reference's strided split) into P device pools whose rounds share every launch of the persistent kernel
+    P = max(1, min(int(os.environ.get("TSB200_POOLS", "4")), ev.pools_per_launch(M)))
+    evs = [ev] + [tsb200.NQueensEvaluator(N, 1, M, device=device_index) for _ in range(P - 1)]
+    warm, wtree, wsol = tsb200.nqueens_warmup(N, P * m_HEAD)
+    c = warm.shape[0] // P
+    parts = [np.ascontiguousarray(warm[g:P * c:P]) for g in range(P)]
+    parts[-1] = np.ascontiguousarray(np.concatenate([parts[-1], warm[P * c:]]))  # static_split's remainder rule
+    floor = 2 * m_HEAD  # steal_floor of the persistent kernel's range
+
+    def step2():
+        """the driver's step 2 on resident pools (nq_devpool_multi_rounds): shared launches, dry pools take the oldest
+        half of the fullest one; -> (rounds, children, solutions)"""
+        tot = [0, 0, 0]
+        while True:
+            sizes = [e.pool_size for e in evs]
+            for i, e in enumerate(evs):
+                if sizes[i] < m_HEAD:
+                    v = max(range(P), key=lambda j: sizes[j])
+                    if v != i and sizes[v] >= floor:
+                        e.pool_steal_from(evs[v], m_HEAD)
+                        sizes = [x.pool_size for x in evs]
+            if max(sizes) < m_HEAD:
+                return tot
+            for nr, _np, nc, ns in tsb200.nqueens_pool_run_multi(evs, m_HEAD, M, 2048):
+                tot = [tot[0] + nr, tot[1] + nc, tot[2] + ns]
+
     stream = torch.cuda.ExternalStream(ev.stream, device=dev)
     want = GOLDEN_NQ[N]
     for _ in range(warmup):
@@ -321,22 +352,28 @@ def run_headline_1gpu(steps, warmup, device_index, M=M_HEAD, N=N_HEAD):
     # ---- value: the offload loop on a pool that is already in HBM
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_dev, nodes, rounds = 0.0, 0, 0
-    l0 = ev.kernel_launches
+    n_launches = lambda: sum(e.kernel_launches for e in evs)  # noqa: E731
+    l0 = n_launches()
     torch.cuda.synchronize()
     with ClockSampler(device_index) as clk:
         for _ in range(steps):
-            ev.pool_push(warm)
-            launches_before = ev.kernel_launches
+            for e, part in zip(evs, parts):
+                e.pool_push(part)
+            torch.cuda.synchronize()
+            launches_before = n_launches()
+            # (every launch inside is followed by a stream synchronisation, so the two events bracket all of it
+            # whichever pool's stream a launch went to)
             e0.record(stream)
-            nr, npar, nc, ns = ev.pool_run(m_HEAD, M)
+            nr, nc, ns = step2()
             e1.record(stream)
             torch.cuda.synchronize()
             t_dev += e0.elapsed_time(e1) / 1e3
             nodes += nc
             rounds += nr
-            launches_per_step = ev.kernel_launches - launches_before
-            ev.pool_drain()
-        launches = ev.kernel_launches - l0
+            launches_per_step = n_launches() - launches_before
+            left = sum(e.pool_drain().shape[0] for e in evs)
+            assert wtree + nc + left <= want[0] and ns + wsol <= want[1]
+        launches = n_launches() - l0
         # ---- e2e: the whole search, host in / host out
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -347,10 +384,11 @@ def run_headline_1gpu(steps, warmup, device_index, M=M_HEAD, N=N_HEAD):
             assert (st.explored_tree, st.explored_sol) == want, "search counts differ from the reference's"
         torch.cuda.synchronize()
         t_e2e = time.perf_counter() - t0
-    ev.close()
-    return {"t_dev": t_dev, "nodes": nodes, "rounds": rounds, "t_e2e": t_e2e, "tree": tree, "launches": launches,
+    for e in evs:
+        e.close()
+    return {"pools": P, "t_dev": t_dev, "nodes": nodes, "rounds": rounds, "t_e2e": t_e2e, "tree": tree, "launches": launches,
             "launches_per_step": launches_per_step, "clocks": clk.summary(), "create_ms": t_create * 1e3,
-            "h2d": warm.nbytes, "d2h": 64 + m_HEAD * 21, "offloads": int(st.offloads), "steps": steps}
+            "h2d": warm.nbytes, "d2h": 64 + P * m_HEAD * 21, "offloads": int(st.offloads), "steps": steps}
 
 
 def run_headline_multi(steps, warmup, world, rank, M=M_HEAD, N=N_HEAD):
@@ -384,7 +422,8 @@ def run_headline_multi(steps, warmup, world, rank, M=M_HEAD, N=N_HEAD):
             t_e2e = time.perf_counter() - t0
         out = {"t_dev": t2, "nodes": tree, "t_e2e": t_e2e, "tree": tree, "launches": launches, "clocks": clk.summary(),
                "launches_per_step": launches // steps, "rounds": int(st.offloads) * steps, "offloads": int(st.offloads),
-               "steps": steps, "h2d": 21 * m_HEAD * world, "d2h": (64 + 21 * m_HEAD) * world, "steals": steals / steps,
+               "steps": steps, "h2d": 21 * m_HEAD * 4 * world, "d2h": (64 + 21 * m_HEAD * 4) * world, "steals": steals / steps,
+               "pools": 4,
                "per_gpu_share": shares, "create_ms": None}
     dist_barrier(world, cpu=True)
     return out
@@ -647,18 +686,21 @@ def main():
                              "traffic": None,
                              "traffic_note": "profiles/nq_rounds_r2_ncu.txt (the N=15 search, 171 M nodes, in one launch): "
                                              "0.75 MB read + 4.8 MB written in DRAM — a 2 MB round lives in the 126 MB L2",
-                             "kernel": "nq_rounds_kernel<17> (persistent, cooperative: all rounds of a search in one launch)",
+                             "kernel": "nq_rounds_ll_kernel<17> (persistent, cooperative; four independent pools per "
+                                       "launch, 74 CTAs each, two CTAs per SM)",
                              "bytes_per_launch": h["nodes"] / h["steps"] * NODE_BYTES, "kernel_us": kernel_s * 1e6,
                              "rounds_per_launch": h["rounds"] / h["steps"],
                              "us_per_round": kernel_s * 1e6 / max(1.0, h["rounds"] / h["steps"]),
                              "note": "42 algorithmic bytes per explored node; a round of 50 000 parents moves ~2 MB and "
-                                     "is bound by the two L2 flag exchanges (+ one release fence) that order it after "
-                                     "the previous round (tools/flag_exchange.py), not by HBM — see kernels.* for "
-                                     "the bandwidth-bound kernels"},
+                                     "is a chain of L2 round trips (one count exchange among the pool's CTAs, one "
+                                     "store -> poll hop for the nodes; tools/flag_exchange.py) with ~1 us of work in "
+                                     "between, not HBM-bound; the rounds of the four pools of a GPU overlap (us_per_round "
+                                     "= kernel time / rounds of all pools) — see kernels.* for the bandwidth-bound kernels"},
                 "numa": {"rank0_bound_to_cores_of_its_gpu": numa_cores, "note": "tsb_bind_thread_to_device: every rank (and "
                          "every per-GPU host thread of the multi-GPU search) is pinned to the cores local to its GPU"},
                 "headline": {"explored_tree": GOLDEN_NQ[N_HEAD][0], "explored_sol": GOLDEN_NQ[N_HEAD][1],
                              "counts_match_reference": True, "offloads_per_search": h["offloads"],
+                             "pools_per_gpu": h.get("pools"),
                              "launches_per_search": h["launches_per_step"], "handle_create_ms": h["create_ms"],
                              "steals_per_search": h.get("steals"), "per_gpu_share": h.get("per_gpu_share")}}
 

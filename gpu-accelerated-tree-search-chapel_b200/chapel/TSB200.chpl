@@ -73,7 +73,7 @@ module TSB200 {
                               ref n_parents: uint(64), ref n_children: uint(64), ref n_solutions: uint(64)): c_int;
   extern proc tsb_nq_pool_run_multi(handles: c_ptr(c_ptr(tsb_nq)), n_pools: c_int, m: c_int, M: c_int,
                                     max_rounds: int(64), outCounts: c_ptr(uint(64))): c_int;
-  extern proc tsb_nq_sibling(h: c_ptr(tsb_nq), ref sibling: c_ptr(tsb_nq)): c_int;
+  extern proc tsb_nq_sibling(h: c_ptr(tsb_nq), index: c_int, ref sibling: c_ptr(tsb_nq)): c_int;
   extern proc tsb_nq_pools_per_launch(h: c_ptr(tsb_nq), M: c_int): c_int;
   extern proc tsb_nq_pool_drain(h: c_ptr(tsb_nq), nodes: c_ptr(void), capacity_nodes: int(64),
                                 ref n: int(64)): c_int;

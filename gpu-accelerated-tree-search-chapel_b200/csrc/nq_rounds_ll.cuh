@@ -25,7 +25,9 @@
 // Measured alternatives for the one remaining exchange (all ~130 CTAs polling the 2 G count words: 2 500-4 000 cycles):
 // a dedicated aggregator CTA that scans the counts and writes every worker its own result line (two contention-free
 // hops: 2 900-3 400 cycles, no gain), per-reader rows that only their owner polls (no gain at 128 CTAs), CTAs of 512
-// threads (slower scan), fewer CTAs (cheaper exchange, more work per CTA: best at 128 of 148 SMs).
+// threads (slower scan), fewer CTAs (cheaper exchange, more work per CTA: best at 128 of 148 SMs), a sentinel
+// poll (one lane per warp watches one piece and the full sweeps start when it has arrived: the extra hop costs more
+// than the poll traffic it saves, 3-12 % slower with one to four pools).
 //
 // The plain 21-byte arena is converted
 // to and from the fat arena by nq_fat_import / nq_fat_export (whole pool, only when the host needs the plain form:
@@ -36,9 +38,11 @@
 namespace tsb {
 
 constexpr int LL_T = 256;                    // threads per CTA
-constexpr int LL_PPT = 2;                    // parents per worker thread
-constexpr int LL_SLICE = LL_T * LL_PPT;      // parents per CTA per round
-constexpr int LL_CAP = 2048;                 // children per window of the staging buffer
+// parents per worker thread (PPT): 2 with one or two pools per launch (128 / 148 CTAs per pool), 3 with three or four
+// (74 CTAs per pool: a round's count exchange among 74 CTAs costs half of one among 148, tools/flag_exchange.py, and
+// every CTA brings 1.5x the work to hide it behind)
+__host__ __device__ constexpr int ll_slice(int ppt) { return LL_T * ppt; }          // parents per CTA per round
+__host__ __device__ constexpr int ll_cap(int ppt) { return ppt <= 2 ? 2048 : 1024; }  // children per window of the staging buffer
 constexpr int LL_WORDS = 8;                  // 8-byte words per fat node
 constexpr int LL_LAYERS = 1024;              // layers of the pool a CTA tracks (more: the kernel leaves and is relaunched)
 constexpr unsigned LL_TRUSTED = 0u;          // layer epoch of the nodes that were in the pool at launch (epochs start at 1)
@@ -151,11 +155,11 @@ __device__ __forceinline__ bool warp_gather_slots2(const unsigned long long* slo
   return true;
 }
 
-template <int T>
+template <int T, int PPT>
 struct LlSmem {
-  alignas(16) uint32_t parent[T * LL_PPT][8];  // the slice: data32[0..7] of every parent
-  alignas(16) uint32_t stage[LL_CAP][8];       // the window's children: data32[0..7]
-  alignas(16) uint16_t item[T * LL_PPT * 20];  // (record << 5) | slot, in child order
+  alignas(16) uint32_t parent[T * PPT][8];     // the slice: data32[0..7] of every parent
+  alignas(16) uint32_t stage[ll_cap(PPT)][8];  // the window's children: data32[0..7]
+  alignas(16) uint16_t item[T * PPT * 20];     // (record << 5) | slot, in child order
   unsigned long long warp_tot64[T / 32];
   unsigned long long red[3];
   long long lay_start[LL_LAYERS];  // the pool's layers, bottom to top: first position ...
@@ -193,11 +197,12 @@ __device__ __forceinline__ void ll_build_child(const uint32_t (*parent)[8], int 
   c[7] = static_cast<uint32_t>(ca >> 32);
 }
 
-template <int N, int T>
-__global__ void __launch_bounds__(T, 2) nq_rounds_ll_kernel(const __grid_constant__ LlMultiParams mprm) {
+template <int N, int T, int MINB, int PPT>
+__global__ void __launch_bounds__(T, MINB) nq_rounds_ll_kernel(const __grid_constant__ LlMultiParams mprm) {
   const LlParams& prm = mprm.pool[blockIdx.y];
+  constexpr int LL_PPT = PPT, LL_CAP = ll_cap(PPT);
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  LlSmem<T>& sm = *reinterpret_cast<LlSmem<T>*>(smem_raw);
+  LlSmem<T, PPT>& sm = *reinterpret_cast<LlSmem<T, PPT>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int k = blockIdx.x, G = gridDim.x;
   LlSync* const sy = prm.sync;
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(T, 2) nq_rounds_ll_kernel(const __grid_constan
     // critical path; pairing k with 2G-1-k evens the load without knowing it in advance.
     const int G2 = 2 * G;
     const unsigned n32 = static_cast<unsigned>(n), uG2 = static_cast<unsigned>(G2), uk = static_cast<unsigned>(k);
-    // (n <= 512 G and k < G <= 256: the products fit 32 bits — four 64-bit divisions cost 700 cycles per round)
+    // (n <= 768 G and k < G <= 256: the products fit 32 bits — four 64-bit divisions cost 700 cycles per round)
     const int a0 = static_cast<int>(n32 * uk / uG2), len0 = static_cast<int>(n32 * (uk + 1u) / uG2) - a0;
     const int a1 = static_cast<int>(n32 * (uG2 - 1u - uk) / uG2), len1 = static_cast<int>(n32 * (uG2 - uk) / uG2) - a1;
     const int len = len0 + len1;
@@ -274,6 +279,13 @@ __global__ void __launch_bounds__(T, 2) nq_rounds_ll_kernel(const __grid_constan
 #pragma unroll
       for (int j = 0; j < PCS; j++)
         if (t + j * T < 4 * len) pending |= 1u << j;
+      // the epoch node i of my slice was stored with: that of the layer its position lies in (mostly the top one)
+      const auto want_of = [&](int i) {
+        const long long pos = s0 + (i < len0 ? a0 + i : a1 + (i - len0));
+        int L = top;
+        while (L > 0 && sm.lay_start[L] > pos) --L;
+        return sm.lay_epoch[L];
+      };
       while (pending) {
         // all loads of a sweep are issued back to back (a dependent re-poll per piece would serialise 8 L2 round trips)
 #pragma unroll
@@ -286,11 +298,7 @@ __global__ void __launch_bounds__(T, 2) nq_rounds_ll_kernel(const __grid_constan
         for (int j = 0; j < PCS; j++)
           if (pending & (1u << j)) {
             const int pc = t + j * T, i = pc >> 2;
-            // the epoch this node was stored with: that of the layer its position lies in (mostly the top one)
-            const long long pos = s0 + (i < len0 ? a0 + i : a1 + (i - len0));
-            int L = top;
-            while (L > 0 && sm.lay_start[L] > pos) --L;
-            const unsigned want = sm.lay_epoch[L];
+            const unsigned want = want_of(i);
             if (want == LL_TRUSTED || (static_cast<unsigned>(w0[j] >> 32) == want && static_cast<unsigned>(w1[j] >> 32) == want)) {
               *reinterpret_cast<uint2*>(&sm.parent[i][2 * (pc & 3)]) =
                   make_uint2(static_cast<uint32_t>(w0[j]), static_cast<uint32_t>(w1[j]));

@@ -488,11 +488,12 @@ struct RoundsCtx {
   int ctas = 0;       // grid size (env TSB200_ROUNDS_CTAS; 0 = two CTAs per three SMs: an all-to-all flag exchange
                       // among 148 CTAs costs 2-3x one among 74 (tools/flag_exchange.py), the per-CTA work grows
                       // the other way; measured best around 100 CTAs of 256 threads)
+  int ppt = 0;        // env TSB200_ROUNDS_PPT=3: the 768-parent slices also where 512 would do (experiments)
   int version = 3;    // 3 = the fence-free kernel on the fat arena (nq_rounds_ll.cuh); 2 = nq_rounds.cuh (env TSB200_ROUNDS_V)
   tsb::FatNode* d_fat = nullptr;  // the pool in the self-validating 64-byte format, while the LL kernel owns it
   long long fat_cap = 0;
   bool in_fat = false;            // the pool currently lives in d_fat (the plain arena is stale)
-  bool attr_ll = false;
+  bool attr_llv[3] = {false, false, false};
   tsb::LlSync* d_ll = nullptr;
   int ensure_fat(long long cap, cudaStream_t s) {
     if (!d_ll) {
@@ -518,13 +519,16 @@ struct RoundsCtx {
     aux_cap = cap;
     return TSB_OK;
   }
-  int ensure(cudaStream_t s) {
+  RoundsCtx() {
     if (const char* v = std::getenv("TSB200_ROUNDS_THREADS")) {
       const int x = std::atoi(v);
       if (x == 256 || x == 512) threads = x;
     }
     if (const char* v = std::getenv("TSB200_ROUNDS_CTAS")) ctas = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("TSB200_ROUNDS_PPT")) ppt = std::atoi(v) == 3 ? 3 : 0;
     if (const char* v = std::getenv("TSB200_ROUNDS_V")) version = std::atoi(v) == 2 ? 2 : 3;
+  }
+  int ensure(cudaStream_t s) {
     if (!d_sync) {
       TSB_CUDA(cudaMalloc(&d_sync, sizeof(tsb::RoundsSync)));
       TSB_CUDA(cudaMemsetAsync(d_sync, 0, sizeof(tsb::RoundsSync), s));
@@ -552,7 +556,7 @@ struct RoundsCtx {
 };
 
 struct tsb_nq : Base {
-  tsb_nq* sibling = nullptr;  // a second pool on the same device, owned by this handle (tsb_nq_sibling)
+  tsb_nq* sibling[3] = {nullptr, nullptr, nullptr};  // further pools on the same device, owned by this handle (tsb_nq_sibling)
   bool aux_ok = false;  // every node of the pool has its side word (nq_expand2.cuh)
   int N = 0, g = 1;
   RoundsCtx rounds;
@@ -1206,8 +1210,10 @@ int tsb_nq_create(tsb_nq** out, int device, int N, int g, int M_max) {
 
 void tsb_nq_destroy(tsb_nq* h) {
   if (!h) return;
-  if (h->sibling) tsb_nq_destroy(h->sibling);
-  h->sibling = nullptr;
+  for (tsb_nq*& x : h->sibling) {
+    if (x) tsb_nq_destroy(x);
+    x = nullptr;
+  }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->ex.release();
@@ -1429,12 +1435,18 @@ int nq_rounds_launch(tsb_nq* h, const tsb::RoundsParams& prm, int grid, cudaStre
   return TSB_EINVAL;
 }
 template <int N>
-int nq_ll_launch_n(tsb_nq* h, const tsb::LlMultiParams& prm, int grid, int pools, cudaStream_t s) {
-  auto kernel = tsb::nq_rounds_ll_kernel<N, tsb::LL_T>;
-  const size_t smem = sizeof(tsb::LlSmem<tsb::LL_T>) + 128;
-  if (!h->rounds.attr_ll) {
+int nq_ll_launch_n(tsb_nq* h, const tsb::LlMultiParams& prm, int grid, int pools, int ppt, cudaStream_t s) {
+  // (one pool: the 160-register build, one CTA per SM; several: capped at 128 registers for two CTAs per SM; three
+  // or four pools: 74 CTAs per pool with 768 parents each, see ll_slice)
+  const int var = pools == 1 ? 0 : ppt == 2 ? 1 : 2;
+  auto kernel = var == 0   ? tsb::nq_rounds_ll_kernel<N, tsb::LL_T, 1, 2>
+                : var == 1 ? tsb::nq_rounds_ll_kernel<N, tsb::LL_T, 2, 2>
+                           : tsb::nq_rounds_ll_kernel<N, tsb::LL_T, 2, 3>;
+  const size_t smem = (var == 2 ? sizeof(tsb::LlSmem<tsb::LL_T, 3>) : sizeof(tsb::LlSmem<tsb::LL_T, 2>)) + 128;
+  bool& attr = h->rounds.attr_llv[var];
+  if (!attr) {
     TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    h->rounds.attr_ll = true;
+    attr = true;
   }
   void* args[] = {const_cast<tsb::LlMultiParams*>(&prm)};
   // cooperative: all CTAs of all pools co-resident (two per SM when there are two pools), or the launch fails
@@ -1452,11 +1464,11 @@ int nq_ll_import_n(tsb_nq* h, long long size, cudaStream_t s) {
   }
   return TSB_OK;
 }
-int nq_ll_launch(tsb_nq* h, const tsb::LlMultiParams& prm, int grid, int pools, cudaStream_t s) {
+int nq_ll_launch(tsb_nq* h, const tsb::LlMultiParams& prm, int grid, int pools, int ppt, cudaStream_t s) {
   switch (h->N) {
 #define TSB_NQ_CASE(n) \
   case n:              \
-    return nq_ll_launch_n<n>(h, prm, grid, pools, s);
+    return nq_ll_launch_n<n>(h, prm, grid, pools, ppt, s);
     TSB_NQ_CASE(1) TSB_NQ_CASE(2) TSB_NQ_CASE(3) TSB_NQ_CASE(4) TSB_NQ_CASE(5) TSB_NQ_CASE(6) TSB_NQ_CASE(7)
     TSB_NQ_CASE(8) TSB_NQ_CASE(9) TSB_NQ_CASE(10) TSB_NQ_CASE(11) TSB_NQ_CASE(12) TSB_NQ_CASE(13)
     TSB_NQ_CASE(14) TSB_NQ_CASE(15) TSB_NQ_CASE(16) TSB_NQ_CASE(17) TSB_NQ_CASE(18) TSB_NQ_CASE(19)
@@ -1498,19 +1510,28 @@ bool env_no_rounds() {
   const char* v = std::getenv("TSB200_NO_ROUNDS");
   return v && *v && *v != '0';
 }
-// grid (CTAs per pool) of the persistent kernel for chunks of up to M parents; 0: M is too large for it
-int nq_ll_grid(const tsb_nq* h, int M) {
-  int grid = std::min(h->di.sms, static_cast<int>(tsb::RND_MAX_CTAS));
-  grid = h->rounds.ctas > 0 ? std::min(grid, h->rounds.ctas) : std::max(1, (grid * 7 / 8) & ~1);  // measured best at 128 of 148 SMs
-  while (static_cast<long long>(grid) * tsb::LL_SLICE < M && grid < h->di.sms) ++grid;  // (M decides)
-  if (static_cast<long long>(M) > static_cast<long long>(grid) * tsb::LL_SLICE || !h->di.coop || env_no_rounds()) return 0;
-  return grid;
+// grid (CTAs per pool) of the persistent kernel for chunks of up to M parents when one launch serves `pools` pools;
+// 0: M is too large for it.  Measured on the N = 17 search at M = 50000 (B200, 148 SMs): one pool: best at 128 CTAs
+// (one per SM); two pools: 148 + 148 (two CTAs per SM; 128 + 128: 6 % slower); four pools: 74 CTAs each.
+// *ppt: parents per thread of the kernel variant to launch (2, or 3 when the pool's CTAs would not cover M with 2).
+int nq_ll_grid(const tsb_nq* h, int M, int pools, int* ppt = nullptr) {
+  if (!h->di.coop || env_no_rounds() || pools < 1 || pools > tsb::LL_MAX_POOLS) return 0;
+  const int sms = std::min(h->di.sms, static_cast<int>(tsb::RND_MAX_CTAS));
+  const int most = pools == 1 ? sms : 2 * sms / pools;  // two CTAs per SM in all
+  int per = static_cast<long long>(most) * tsb::ll_slice(2) >= M ? 2 : 3;
+  if (pools > 1 && h->rounds.ppt == 3) per = 3;
+  const int slice = tsb::ll_slice(per);
+  int grid = pools == 1 ? std::max(1, (sms * 7 / 8) & ~1) : most;
+  if (h->rounds.ctas > 0) grid = std::min(most, h->rounds.ctas);
+  while (static_cast<long long>(grid) * slice < M && grid < most) ++grid;  // (M decides)
+  if (ppt) *ppt = per;
+  return static_cast<long long>(M) <= static_cast<long long>(grid) * slice && (pools > 1 || per == 2) ? grid : 0;
 }
 // Up to `max_rounds` rounds of EACH of the K pools (handles on one device, same N) in launches of the persistent
 // kernel that serve all pools that still have work: grid (grid, pools).  out[4 i ..] += {rounds, parents, children,
 // solutions} of pool i.  A pool leaves the launch on its own (done, round budget, arena full, layer table full); the
 // launch ends when every pool has left, the pools that stopped for room grow and go again.
-int nq_ll_run_multi(tsb_nq* const* hs, int K, int m, int M, int grid, int64_t max_rounds, uint64_t* out) {
+int nq_ll_run_multi(tsb_nq* const* hs, int K, int m, int M, int64_t max_rounds, uint64_t* out) {
   int64_t left[tsb::LL_MAX_POOLS];
   bool active[tsb::LL_MAX_POOLS];
   for (int i = 0; i < K; i++) {
@@ -1567,7 +1588,11 @@ int nq_ll_run_multi(tsb_nq* const* hs, int K, int m, int M, int grid, int64_t ma
     }
     if (n_act == 0) break;
     tsb_nq* h0 = hs[map[0]];
-    int rc = nq_ll_launch(h0, mp, grid, n_act, h0->stream);
+    // (variant and grid follow the number of pools that still run: a lone survivor gets the one-pool kernel)
+    int ppt = 2;
+    const int grid = nq_ll_grid(h0, M, n_act, &ppt);
+    if (grid == 0) return TSB_EINVAL;  // (checked by the callers for K pools, and fewer pools fit a fortiori)
+    int rc = nq_ll_launch(h0, mp, grid, n_act, ppt, h0->stream);
     if (rc != TSB_OK) return rc;
     TSB_CUDA(cudaStreamSynchronize(h0->stream));
     for (int a = 0; a < n_act; a++) {
@@ -1641,11 +1666,11 @@ int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rou
     return TSB_OK;
   }
   nq_pool_setup(h);
-  if (h->rounds.version == 3 && static_cast<long long>(M) <= static_cast<long long>(grid) * tsb::LL_SLICE) {
+  if (h->rounds.version == 3 && nq_ll_grid(h, M, 1) > 0) {
     // ---- the fence-free kernel on the fat arena (nq_rounds_ll.cuh)
     uint64_t out[4] = {0, 0, 0, 0};
     tsb_nq* one[1] = {h};
-    rc = nq_ll_run_multi(one, 1, m, M, grid, max_rounds, out);
+    rc = nq_ll_run_multi(one, 1, m, M, max_rounds, out);
     *n_rounds = out[0];
     *n_parents = out[1];
     *n_children = out[2];
@@ -1710,20 +1735,21 @@ int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rou
   return TSB_OK;
 }
 
-int tsb_nq_sibling(tsb_nq* h, tsb_nq** sibling) {
-  if (!h || !sibling) return TSB_EINVAL;
-  if (!h->sibling) {
-    int rc = tsb_nq_create(&h->sibling, h->device, h->N, h->g, h->M_max);
+int tsb_nq_sibling(tsb_nq* h, int index, tsb_nq** sibling) {
+  if (!h || !sibling || index < 1 || index >= tsb::LL_MAX_POOLS) return TSB_EINVAL;
+  if (!h->sibling[index - 1]) {
+    int rc = tsb_nq_create(&h->sibling[index - 1], h->device, h->N, h->g, h->M_max);
     if (rc != TSB_OK) return rc;
   }
-  *sibling = h->sibling;
+  *sibling = h->sibling[index - 1];
   return TSB_OK;
 }
 
 int tsb_nq_pools_per_launch(const tsb_nq* h, int M) {
   if (!h || M < 1 || M > h->M_max || h->rounds.version != 3) return 1;
-  const int grid = nq_ll_grid(h, M);
-  return grid > 0 && grid <= h->di.sms ? 2 : 1;  // (two co-resident CTAs per SM, one of each pool)
+  for (int pools = tsb::LL_MAX_POOLS; pools > 1; pools--)
+    if (nq_ll_grid(h, M, pools) > 0) return pools;
+  return 1;
 }
 
 int tsb_nq_pool_run_multi(tsb_nq* const* handles, int n_pools, int m, int M, int64_t max_rounds, uint64_t* out) {
@@ -1736,16 +1762,15 @@ int tsb_nq_pool_run_multi(tsb_nq* const* handles, int n_pools, int m, int M, int
   }
   std::memset(out, 0, sizeof(uint64_t) * 4 * n_pools);
   TSB_CUDA(cudaSetDevice(handles[0]->device));
-  const int grid = handles[0]->rounds.version == 3 ? nq_ll_grid(handles[0], M) : 0;
-  // two pools need two co-resident CTAs per SM; chunks too large for the persistent kernel: one pool after the other
-  if (grid == 0 || (n_pools > 1 && static_cast<long long>(grid) * n_pools > 2LL * handles[0]->di.sms)) {
+  const int grid = handles[0]->rounds.version == 3 ? nq_ll_grid(handles[0], M, n_pools) : 0;
+  if (grid == 0) {  // chunks too large for the persistent kernel with this many pools: one pool after the other
     for (int i = 0; i < n_pools; i++) {
       int rc = tsb_nq_pool_run(handles[i], m, M, max_rounds, &out[4 * i], &out[4 * i + 1], &out[4 * i + 2], &out[4 * i + 3]);
       if (rc != TSB_OK) return rc;
     }
     return TSB_OK;
   }
-  return nq_ll_run_multi(handles, n_pools, m, M, grid, max_rounds, out);
+  return nq_ll_run_multi(handles, n_pools, m, M, max_rounds, out);
 }
 
 int tsb_nq_pool_steal(tsb_nq* victim, tsb_nq* thief, int m, int64_t* n_stolen) {
@@ -1863,7 +1888,11 @@ int tsb_nq_set_xfer(tsb_nq* h, int mode) {
   return TSB_OK;
 }
 uint64_t tsb_nq_kernel_launches(const tsb_nq* h) {
-  return h ? h->launches + (h->sibling ? h->sibling->launches : 0) : 0;
+  if (!h) return 0;
+  uint64_t n = h->launches;
+  for (const tsb_nq* x : h->sibling)
+    if (x) n += x->launches;
+  return n;
 }
 void* tsb_nq_stream(const tsb_nq* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
 

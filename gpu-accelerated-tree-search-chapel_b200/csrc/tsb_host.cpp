@@ -313,53 +313,68 @@ void nq_devpool_rounds(tsb_nq* h, int m, int M, StealBoard* sb, int me, GpuTaskR
   }
   if (r.rc != TSB_OK) board_abort(sb, me);
 }
-// Two pools per task (TSB200_POOLS=1 turns it off): for chunks that fit the persistent kernel a round is a chain of
-// L2 round trips with ~1 us of work in between, so the task's share of the warm-up pool is split once more — the
-// reference's own strided split (static_split) — into two device pools whose rounds run in ONE launch
-// (tsb_nq_pool_run_multi), a CTA of each on every SM filling the other's waits.  Each pool follows the reference's
-// rule on its own nodes: for D tasks the chunk sequence is that of a 2-level split into 2 D pools, the totals are
-// split-invariant.  When one pool of the pair runs dry it takes the oldest half of the other (as between tasks).
+// Several pools per task (TSB200_POOLS=1 turns it off, =2 caps it at two): for chunks that fit the persistent kernel a
+// round is a chain of L2 round trips with ~1 us of work in between, so the task's share of the warm-up pool is split
+// once more — the reference's own strided split (static_split) — into P device pools (P = tsb_nq_pools_per_launch: 4
+// on a B200 for M <= 56832) whose rounds run in ONE launch (tsb_nq_pool_run_multi), two CTAs of different pools on
+// every SM filling each other's waits.  Each pool follows the reference's rule on its own nodes: for D tasks the
+// chunk sequence is that of a 2-level split into P D pools, the totals are split-invariant.  A pool of the group
+// that runs dry takes the oldest half of the fullest one (as between tasks).
 inline int nq_pools_wanted(int M) {  // (decides the warm-up size, before any handle exists)
-  const char* v = std::getenv("TSB200_POOLS");
-  if (v && std::atoi(v) == 1) return 1;
-  return M <= 65536 ? 2 : 1;  // 512 parents x 128 CTAs: the persistent kernel's range
+  int cap = 4;
+  if (const char* v = std::getenv("TSB200_POOLS")) cap = std::max(1, std::min(4, std::atoi(v)));
+  // the persistent kernel's ranges on 148 SMs: 768 parents x 74 CTAs (four pools), 768 x 98 (three), 512 x 148 (two)
+  const int fit = M <= 56832 ? 4 : M <= 75264 ? 3 : M <= 75776 ? 2 : 1;
+  return std::min(cap, fit);
 }
-inline bool nq_pair_mode(tsb_nq* h, int M) { return nq_pools_wanted(M) == 2 && tsb_nq_pools_per_launch(h, M) >= 2; }
-void nq_devpool_pair_rounds(tsb_nq* h, tsb_nq* sib, int m, int M, StealBoard* sb, int me, GpuTaskResult& r) {
+inline int nq_pools_of(tsb_nq* h, int M) { return std::min(nq_pools_wanted(M), tsb_nq_pools_per_launch(h, M)); }
+void nq_devpool_multi_rounds(std::vector<tsb_nq*>& hs, int m, int M, StealBoard* sb, int me, GpuTaskResult& r) {
   const bool no_steal = [] {
     const char* v = std::getenv("TSB200_NO_STEAL");
     return v && *v && *v != '0';
   }();
-  tsb_nq* pair[2] = {h, sib};
-  // a thief task is served from the fuller pool of the pair
+  const int P = static_cast<int>(hs.size());
+  const auto fullest = [&] {
+    int v = 0;
+    for (int i = 1; i < P; i++)
+      if (tsb_nq_pool_size(hs[i]) > tsb_nq_pool_size(hs[v])) v = i;
+    return v;
+  };
+  // a thief task is served from the fullest pool of the group
   const auto steal = [&](void*, void* t, int64_t* got) {
-    tsb_nq* v = tsb_nq_pool_size(h) >= tsb_nq_pool_size(sib) ? h : sib;
-    return tsb_nq_pool_steal(v, static_cast<tsb_nq*>(t), m, got);
+    return tsb_nq_pool_steal(hs[fullest()], static_cast<tsb_nq*>(t), m, got);
   };
   const long long floor_ = steal_floor(m, M);
+  std::vector<uint64_t> out(4 * P);
   while (r.rc == TSB_OK) {
-    long long a = tsb_nq_pool_size(h), b = tsb_nq_pool_size(sib);
-    if (!no_steal && ((a < m && b >= floor_) || (b < m && a >= floor_))) {  // balance inside the pair
-      int64_t got = 0;
-      r.rc = a < m ? tsb_nq_pool_steal(sib, h, m, &got) : tsb_nq_pool_steal(h, sib, m, &got);
+    if (!no_steal) {  // balance inside the group: every dry pool takes half of the fullest one
+      for (int i = 0; i < P && r.rc == TSB_OK; i++) {
+        if (tsb_nq_pool_size(hs[i]) >= m) continue;
+        const int v = fullest();
+        if (v == i || tsb_nq_pool_size(hs[v]) < floor_) break;
+        int64_t got = 0;
+        r.rc = tsb_nq_pool_steal(hs[v], hs[i], m, &got);
+      }
       if (r.rc != TSB_OK) break;
-      a = tsb_nq_pool_size(h);
-      b = tsb_nq_pool_size(sib);
     }
-    if (a < m && b < m) {
-      if (!board_acquire(sb, me, a + b, floor_)) break;
+    long long most = 0, total = 0;
+    for (tsb_nq* x : hs) {
+      most = std::max<long long>(most, tsb_nq_pool_size(x));
+      total += tsb_nq_pool_size(x);
+    }
+    if (most < m) {
+      if (!board_acquire(sb, me, total, floor_)) break;
       continue;
     }
-    uint64_t out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    r.rc = tsb_nq_pool_run_multi(pair, 2, m, M, sb ? rounds_per_call(sb, M) : 2048, out);
+    r.rc = tsb_nq_pool_run_multi(hs.data(), P, m, M, sb ? rounds_per_call(sb, M) : 2048, out.data());
     if (r.rc != TSB_OK) break;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < P; i++) {
       r.offloads += out[4 * i];
       r.parents += out[4 * i + 1];
       r.tree += out[4 * i + 2];
       r.sol += out[4 * i + 3];
     }
-    r.rc = board_service(sb, me, std::max(tsb_nq_pool_size(h), tsb_nq_pool_size(sib)), floor_, steal);
+    r.rc = board_service(sb, me, tsb_nq_pool_size(hs[fullest()]), floor_, steal);
   }
   if (r.rc != TSB_OK) board_abort(sb, me);
 }
@@ -367,15 +382,23 @@ void nq_devpool_pair_rounds(tsb_nq* h, tsb_nq* sib, int m, int M, StealBoard* sb
 void nq_devpool_on(tsb_nq* h, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResult& r, StealBoard* sb = nullptr,
                    int me = 0) {
   const uint64_t l0 = tsb_nq_kernel_launches(h);
-  tsb_nq* sib = nullptr;
-  if (nq_pair_mode(h, M) && tsb_nq_sibling(h, &sib) == TSB_OK && sib) {
-    std::vector<Pool<tsb_nq_node>> half;
-    static_split(pool, 2, half);
-    r.rc = tsb_nq_pool_push(h, &half[0].el[half[0].front], static_cast<int64_t>(half[0].size));
-    if (r.rc == TSB_OK) r.rc = tsb_nq_pool_push(sib, &half[1].el[half[1].front], static_cast<int64_t>(half[1].size));
-    if (sb) sb->publish_handle(me, r.rc == TSB_OK ? h : nullptr, std::max(tsb_nq_pool_size(h), tsb_nq_pool_size(sib)));
-    if (r.rc == TSB_OK) nq_devpool_pair_rounds(h, sib, m, M, sb, me, r);
-    for (tsb_nq* x : {h, sib}) {
+  if (const int P = nq_pools_of(h, M); P > 1) {
+    std::vector<tsb_nq*> hs{h};
+    for (int i = 1; i < P && r.rc == TSB_OK; i++) {
+      tsb_nq* sib = nullptr;
+      r.rc = tsb_nq_sibling(h, i, &sib);
+      hs.push_back(sib);
+    }
+    std::vector<Pool<tsb_nq_node>> part;
+    if (r.rc == TSB_OK) static_split(pool, P, part);
+    long long most = 0;
+    for (int i = 0; i < P && r.rc == TSB_OK; i++) {
+      r.rc = tsb_nq_pool_push(hs[i], &part[i].el[part[i].front], static_cast<int64_t>(part[i].size));
+      most = std::max<long long>(most, tsb_nq_pool_size(hs[i]));
+    }
+    if (sb) sb->publish_handle(me, r.rc == TSB_OK ? h : nullptr, most);
+    if (r.rc == TSB_OK) nq_devpool_multi_rounds(hs, m, M, sb, me, r);
+    for (tsb_nq* x : hs) {
       if (r.rc != TSB_OK) break;
       const int64_t left = tsb_nq_pool_size(x);
       std::vector<tsb_nq_node> rest(static_cast<size_t>(left) + 1);

@@ -112,6 +112,10 @@ class NQueensEvaluator:
         check(lib().tsb_nq_pool_steal(victim._h, self._h, m, C.byref(got)), "tsb_nq_pool_steal")
         return int(got.value)
 
+    def pools_per_launch(self, M: int) -> int:
+        """pools one launch of the persistent kernel serves best for chunks of M parents (tsb_nq_pools_per_launch)"""
+        return int(lib().tsb_nq_pools_per_launch(self._h, M))
+
     def pool_run(self, m: int, M: int, max_rounds: int = 2**62):
         """(rounds, parents popped, children appended, solutions) of up to max_rounds device-side offload rounds
         (until the pool holds fewer than m nodes); one persistent kernel for M <= 512 x #SMs"""

@@ -159,11 +159,12 @@ int tsb_nq_pool_run(tsb_nq* h, int m, int M, int64_t max_rounds, uint64_t* n_rou
  * pools living on one GPU.  out[4 i .. 4 i + 3] = {rounds, parents, children, solutions} of pool i.  Chunks too large
  * for the persistent kernel: the pools are run one after the other. */
 int tsb_nq_pool_run_multi(tsb_nq* const* handles, int n_pools, int m, int M, int64_t max_rounds, uint64_t* out);
-/* A second, independent pool on the same device, created on first use and owned by `h` (destroyed with it; its
- * launches are included in h's tsb_nq_kernel_launches count): what a driver pairs with `h` in tsb_nq_pool_run_multi. */
-int tsb_nq_sibling(tsb_nq* h, tsb_nq** sibling);
-/* How many pools one launch of the persistent kernel can serve for chunks of up to M parents on h's device: 2 when
- * M fits the persistent kernel (two co-resident CTAs per SM), else 1. */
+/* Further independent pools on the same device (index 1..3), created on first use and owned by `h` (destroyed with
+ * it; their launches are included in h's tsb_nq_kernel_launches count): what a driver groups with `h` in
+ * tsb_nq_pool_run_multi. */
+int tsb_nq_sibling(tsb_nq* h, int index, tsb_nq** sibling);
+/* How many pools one launch of the persistent kernel serves best for chunks of up to M parents on h's device: 4
+ * (74 CTAs of 768 parents per pool on a B200), 2 (148 + 148 CTAs of 512), or 1 (M beyond the persistent kernel). */
 int tsb_nq_pools_per_launch(const tsb_nq* h, int M);
 
 /* page-lock + map a caller-owned host array for the lifetime of the handle (see the header comment);

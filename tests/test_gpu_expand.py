@@ -101,23 +101,25 @@ def test_device_resident_search_counts(golden_dir, N, m, M, D, monkeypatch):
         assert st.kernel_launches == 2 * st.offloads  # count, build
 
 
-@pytest.mark.parametrize("N,m,M", [(10, 25, 50000), (12, 5, 300), (13, 25, 4096), (14, 25, 50000), (15, 25, 50000)])
-def test_two_pools_per_task_is_the_reference_split_into_two_tasks(golden_dir, N, m, M, monkeypatch):
+@pytest.mark.parametrize("N,m,M,P", [(10, 25, 50000, 4), (12, 5, 300, 4), (13, 25, 4096, 2), (14, 25, 50000, 4),
+                                     (15, 25, 50000, 2), (15, 25, 50000, 4), (14, 25, 60000, 4)])
+def test_several_pools_per_task_is_the_reference_split_into_as_many_tasks(golden_dir, N, m, M, P, monkeypatch):
     """default for chunks that fit the persistent kernel: the task's pool is split once more (the reference's strided
-    split) into two device pools whose rounds share one launch (tsb_nq_pool_run_multi).  Without stealing, D = 1 is
-    then exactly the reference's D = 2 run: same warm-up, same split, same chunk sequence in each pool"""
+    split) into P device pools whose rounds share one launch (tsb_nq_pool_run_multi; P = 4 for M <= 56832, else 3).
+    Without stealing, D = 1 is then exactly the reference's D = P run: same warm-up, same split, same chunk sequence
+    in each pool"""
     monkeypatch.setenv("TSB200_NO_STEAL", "1")
-    monkeypatch.delenv("TSB200_POOLS", raising=False)
+    monkeypatch.setenv("TSB200_POOLS", str(P))
     counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
     st = tsb200.nqueens_search_device(N, 1, m, M, 1)
     assert (st.explored_tree, st.explored_sol) == (counts["tree"], counts["sol"])
-    ref = po.nq_search_offload(N, 1, m, M, 2)
+    ref = po.nq_search_offload(N, 1, m, M, P if M <= 56832 else 3)
     assert (st.offloads, st.offloaded_parents) == (ref.offloads, ref.offloaded_parents)
     assert 0 < st.kernel_launches < max(24, st.offloads // 4 + 24)
 
 
 @pytest.mark.parametrize("N,m,M,D", [(13, 25, 2000, 1), (15, 25, 50000, 1), (14, 25, 50000, 3), (15, 25, 30000, 8)])
-def test_two_pools_per_task_with_stealing_totals(golden_dir, N, m, M, D, monkeypatch):
+def test_several_pools_per_task_with_stealing_totals(golden_dir, N, m, M, D, monkeypatch):
     monkeypatch.delenv("TSB200_POOLS", raising=False)
     monkeypatch.delenv("TSB200_NO_STEAL", raising=False)
     counts = json.load(open(os.path.join(golden_dir, "counts.json")))["nqueens"][str(N)]
