@@ -42,7 +42,9 @@ constexpr int LL_T = 256;                    // threads per CTA
 // (74 CTAs per pool: a round's count exchange among 74 CTAs costs half of one among 148, tools/flag_exchange.py, and
 // every CTA brings 1.5x the work to hide it behind)
 __host__ __device__ constexpr int ll_slice(int ppt) { return LL_T * ppt; }          // parents per CTA per round
-__host__ __device__ constexpr int ll_cap(int ppt) { return ppt <= 2 ? 2048 : 1024; }  // children per window of the staging buffer
+// children per window of the staging buffer (a CTA's share of a round averages ~0.8 children per parent; a dense
+// share takes several windows); 512 in the three-CTAs-per-SM build (MINB = 3: 64 KB of shared memory per CTA)
+__host__ __device__ constexpr int ll_cap(int ppt, int minb) { return minb >= 3 ? 512 : ppt <= 2 ? 2048 : 1024; }
 constexpr int LL_WORDS = 8;                  // 8-byte words per fat node
 constexpr int LL_LAYERS = 1024;              // layers of the pool a CTA tracks (more: the kernel leaves and is relaunched)
 constexpr unsigned LL_TRUSTED = 0u;          // layer epoch of the nodes that were in the pool at launch (epochs start at 1)
@@ -155,10 +157,10 @@ __device__ __forceinline__ bool warp_gather_slots2(const unsigned long long* slo
   return true;
 }
 
-template <int T, int PPT>
+template <int T, int PPT, int MINB>
 struct LlSmem {
-  alignas(16) uint32_t parent[T * PPT][8];     // the slice: data32[0..7] of every parent
-  alignas(16) uint32_t stage[ll_cap(PPT)][8];  // the window's children: data32[0..7]
+  alignas(16) uint32_t parent[T * PPT][8];           // the slice: data32[0..7] of every parent
+  alignas(16) uint32_t stage[ll_cap(PPT, MINB)][8];  // the window's children: data32[0..7]
   alignas(16) uint16_t item[T * PPT * 20];     // (record << 5) | slot, in child order
   unsigned long long warp_tot64[T / 32];
   unsigned long long red[3];
@@ -200,9 +202,9 @@ __device__ __forceinline__ void ll_build_child(const uint32_t (*parent)[8], int 
 template <int N, int T, int MINB, int PPT>
 __global__ void __launch_bounds__(T, MINB) nq_rounds_ll_kernel(const __grid_constant__ LlMultiParams mprm) {
   const LlParams& prm = mprm.pool[blockIdx.y];
-  constexpr int LL_PPT = PPT, LL_CAP = ll_cap(PPT);
+  constexpr int LL_PPT = PPT, LL_CAP = ll_cap(PPT, MINB);
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  LlSmem<T, PPT>& sm = *reinterpret_cast<LlSmem<T, PPT>*>(smem_raw);
+  LlSmem<T, PPT, MINB>& sm = *reinterpret_cast<LlSmem<T, PPT, MINB>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int k = blockIdx.x, G = gridDim.x;
   LlSync* const sy = prm.sync;

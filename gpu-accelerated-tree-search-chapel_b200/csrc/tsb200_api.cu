@@ -488,12 +488,13 @@ struct RoundsCtx {
   int ctas = 0;       // grid size (env TSB200_ROUNDS_CTAS; 0 = two CTAs per three SMs: an all-to-all flag exchange
                       // among 148 CTAs costs 2-3x one among 74 (tools/flag_exchange.py), the per-CTA work grows
                       // the other way; measured best around 100 CTAs of 256 threads)
+  int occ = 2;        // env TSB200_ROUNDS_OCC=3: three CTAs per SM (several pools per launch)
   int ppt = 0;        // env TSB200_ROUNDS_PPT=3: the 768-parent slices also where 512 would do (experiments)
   int version = 3;    // 3 = the fence-free kernel on the fat arena (nq_rounds_ll.cuh); 2 = nq_rounds.cuh (env TSB200_ROUNDS_V)
   tsb::FatNode* d_fat = nullptr;  // the pool in the self-validating 64-byte format, while the LL kernel owns it
   long long fat_cap = 0;
   bool in_fat = false;            // the pool currently lives in d_fat (the plain arena is stale)
-  bool attr_llv[3] = {false, false, false};
+  bool attr_llv[4] = {false, false, false, false};
   tsb::LlSync* d_ll = nullptr;
   int ensure_fat(long long cap, cudaStream_t s) {
     if (!d_ll) {
@@ -526,6 +527,7 @@ struct RoundsCtx {
     }
     if (const char* v = std::getenv("TSB200_ROUNDS_CTAS")) ctas = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("TSB200_ROUNDS_PPT")) ppt = std::atoi(v) == 3 ? 3 : 0;
+    if (const char* v = std::getenv("TSB200_ROUNDS_OCC")) occ = std::atoi(v) == 3 ? 3 : 2;
     if (const char* v = std::getenv("TSB200_ROUNDS_V")) version = std::atoi(v) == 2 ? 2 : 3;
   }
   int ensure(cudaStream_t s) {
@@ -1438,11 +1440,16 @@ template <int N>
 int nq_ll_launch_n(tsb_nq* h, const tsb::LlMultiParams& prm, int grid, int pools, int ppt, cudaStream_t s) {
   // (one pool: the 160-register build, one CTA per SM; several: capped at 128 registers for two CTAs per SM; three
   // or four pools: 74 CTAs per pool with 768 parents each, see ll_slice)
-  const int var = pools == 1 ? 0 : ppt == 2 ? 1 : 2;
+  // ppt > 10: the three-CTAs-per-SM build (80 registers, 64 KB of shared memory) with ppt - 10 parents per thread
+  const int var = pools == 1 ? 0 : ppt == 2 ? 1 : ppt == 3 ? 2 : 3;
   auto kernel = var == 0   ? tsb::nq_rounds_ll_kernel<N, tsb::LL_T, 1, 2>
                 : var == 1 ? tsb::nq_rounds_ll_kernel<N, tsb::LL_T, 2, 2>
-                           : tsb::nq_rounds_ll_kernel<N, tsb::LL_T, 2, 3>;
-  const size_t smem = (var == 2 ? sizeof(tsb::LlSmem<tsb::LL_T, 3>) : sizeof(tsb::LlSmem<tsb::LL_T, 2>)) + 128;
+                : var == 2 ? tsb::nq_rounds_ll_kernel<N, tsb::LL_T, 2, 3>
+                           : tsb::nq_rounds_ll_kernel<N, tsb::LL_T, 3, 2>;
+  const size_t smem = (var == 0   ? sizeof(tsb::LlSmem<tsb::LL_T, 2, 1>)
+                       : var == 1 ? sizeof(tsb::LlSmem<tsb::LL_T, 2, 2>)
+                       : var == 2 ? sizeof(tsb::LlSmem<tsb::LL_T, 3, 2>)
+                                  : sizeof(tsb::LlSmem<tsb::LL_T, 2, 3>)) + 128;
   bool& attr = h->rounds.attr_llv[var];
   if (!attr) {
     TSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -1517,14 +1524,20 @@ bool env_no_rounds() {
 int nq_ll_grid(const tsb_nq* h, int M, int pools, int* ppt = nullptr) {
   if (!h->di.coop || env_no_rounds() || pools < 1 || pools > tsb::LL_MAX_POOLS) return 0;
   const int sms = std::min(h->di.sms, static_cast<int>(tsb::RND_MAX_CTAS));
-  const int most = pools == 1 ? sms : 2 * sms / pools;  // two CTAs per SM in all
+  int most = pools == 1 ? sms : 2 * sms / pools;  // two CTAs per SM in all
   int per = static_cast<long long>(most) * tsb::ll_slice(2) >= M ? 2 : 3;
   if (pools > 1 && h->rounds.ppt == 3) per = 3;
+  bool occ3 = false;
+  if (pools > 1 && h->rounds.occ == 3 && static_cast<long long>(3 * sms / pools) * tsb::ll_slice(2) >= M) {
+    most = 3 * sms / pools;  // three CTAs per SM in all, 512 parents per CTA
+    per = 2;
+    occ3 = true;
+  }
   const int slice = tsb::ll_slice(per);
   int grid = pools == 1 ? std::max(1, (sms * 7 / 8) & ~1) : most;
   if (h->rounds.ctas > 0) grid = std::min(most, h->rounds.ctas);
   while (static_cast<long long>(grid) * slice < M && grid < most) ++grid;  // (M decides)
-  if (ppt) *ppt = per;
+  if (ppt) *ppt = occ3 ? 12 : per;
   return static_cast<long long>(M) <= static_cast<long long>(grid) * slice && (pools > 1 || per == 2) ? grid : 0;
 }
 // Up to `max_rounds` rounds of EACH of the K pools (handles on one device, same N) in launches of the persistent

@@ -423,12 +423,58 @@ void nq_devpool_on(tsb_nq* h, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResu
   }
   r.launches = tsb_nq_kernel_launches(h) - l0;
 }
+// Handles of the device-pool drivers are kept between searches (per device, N, g, M): a handle with its sibling
+// pools, arenas and fat arenas is ~1.4 GB of cudaMalloc / cudaFree per GPU, which at 8 GPUs cost more than the N = 17
+// search itself.  (The Chapel drivers declare their device arrays once, outside the search loop, as well.)
+// tsb_release_cached_handles frees them.
+struct NqHandleCache {
+  struct Entry {
+    int device, N, g, M;
+    tsb_nq* h;
+  };
+  std::mutex mu;
+  std::vector<Entry> idle;
+  tsb_nq* acquire(int device, int N, int g, int M, int* rc) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t i = 0; i < idle.size(); i++)
+        if (idle[i].device == device && idle[i].N == N && idle[i].g == g && idle[i].M == M) {
+          tsb_nq* h = idle[i].h;
+          idle.erase(idle.begin() + static_cast<long>(i));
+          *rc = TSB_OK;
+          return h;
+        }
+    }
+    tsb_nq* h = nullptr;
+    *rc = tsb_nq_create(&h, device, N, g, M);
+    return *rc == TSB_OK ? h : nullptr;
+  }
+  void release(tsb_nq* h, int device, int N, int g, int M, bool healthy) {
+    if (!h) return;
+    if (!healthy || std::getenv("TSB200_NO_HANDLE_CACHE")) {
+      tsb_nq_destroy(h);
+      return;
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    idle.push_back({device, N, g, M, h});
+  }
+  void clear() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (Entry& e : idle) tsb_nq_destroy(e.h);
+    idle.clear();
+  }
+};
+NqHandleCache& nq_handle_cache() {
+  static NqHandleCache* c = new NqHandleCache();  // (never destroyed: no CUDA calls at process exit)
+  return *c;
+}
+
 void nq_devpool_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResult& r,
                      StealBoard* sb = nullptr, int me = 0) {
   tsb_nq* h = nullptr;
   const bool trace = std::getenv("TSB200_TRACE") != nullptr;
   const double tt0 = now_s();
-  r.rc = tsb_nq_create(&h, device, N, g, M);
+  h = nq_handle_cache().acquire(device, N, g, M, &r.rc);
   if (r.rc != TSB_OK) {
     if (sb) sb->publish_handle(me, nullptr, 0);
     return;
@@ -436,7 +482,7 @@ void nq_devpool_task(int device, int N, int g, int m, int M, Pool<tsb_nq_node>& 
   const double tt1 = now_s();
   nq_devpool_on(h, m, M, pool, r, sb, me);
   const double tt2 = now_s();
-  tsb_nq_destroy(h);
+  nq_handle_cache().release(h, device, N, g, M, r.rc == TSB_OK);
   if (trace) std::fprintf(stderr, "[tsb200] device %d: create %.1f ms, %llu rounds in %.1f ms, destroy %.1f ms\n", device,
                           (tt1 - tt0) * 1e3, static_cast<unsigned long long>(r.offloads), (tt2 - tt1) * 1e3,
                           (now_s() - tt2) * 1e3);
@@ -1000,6 +1046,8 @@ static int pfsp_search_impl(int inst, int lb_kind, int ub, int m, int M, int D, 
 
 // step 1 of the drivers alone (nqueens_gpu_chpl.chpl:169-175): breadth-first from the root until the pool holds
 // min_size nodes; the pool, in order, and what was explored on the way
+void tsb_release_cached_handles(void) { nq_handle_cache().clear(); }
+
 int tsb_nq_warmup(int N, int min_size, void* nodes, int64_t capacity, int64_t* n, uint64_t* tree, uint64_t* sol) {
   if (N < 1 || N > TSB_MAX_QUEENS || min_size < 1 || !n || !tree || !sol || (capacity && !nodes)) return TSB_EINVAL;
   Pool<tsb_nq_node> pool;

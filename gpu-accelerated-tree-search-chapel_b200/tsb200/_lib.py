@@ -83,6 +83,7 @@ SYMBOLS = {
     "tsb_pfsp_pool_steal": (_i, [_vp, _vp, _i, C.POINTER(_i64)]),
     "tsb_nq_pool_run": (_i, [_vp, _i, _i, _i64, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "tsb_nq_pool_run_multi": (_i, [C.POINTER(_vp), _i, _i, _i, _i64, C.POINTER(_u64)]),
+    "tsb_release_cached_handles": (None, []),
     "tsb_nq_sibling": (_i, [_vp, _i, C.POINTER(_vp)]),
     "tsb_nq_pools_per_launch": (_i, [_vp, _i]),
     "tsb_nq_register_host": (_i, [_vp, _vp, C.c_size_t]),

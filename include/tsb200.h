@@ -295,6 +295,9 @@ typedef struct {
 int tsb_nq_warmup(int N, int min_size, void* nodes, int64_t capacity_nodes, int64_t* n, uint64_t* tree, uint64_t* sol);
 /* nqueens_gpu_chpl.chpl:152-248 / nqueens_multigpu_chpl.chpl:158-352 */
 int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out);
+/* tsb_nq_search_device[_part] keep their handles (device pools, arenas) per (device, N, g, M) between calls; this
+ * frees them.  TSB200_NO_HANDLE_CACHE=1: create and destroy per search. */
+void tsb_release_cached_handles(void);
 /* the same 3-step search with the pool(s) of step 2 resident on the device(s) (tsb_nq_pool_*): identical
  * chunk sequence, identical counts; the host only reads three counters per round.  D > 1 = the same static
  * strided split, one device pool per GPU; a task whose pool runs dry steals the oldest half of the fullest device

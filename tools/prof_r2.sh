@@ -15,6 +15,7 @@ cap pfsp_lb2 pfsp_lb2_kernel 3 lb2
 cap nq_count nq_expand_count_kernel 2 expand
 cap nq_build nq_expand_build_kernel 2 expand
 cap nq_rounds nq_rounds_ll_kernel 0 rounds
+cap nq_rounds_pools nq_rounds_ll_kernel 0 rounds17
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_r2.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu_r2.json 2> gpurun_out/bench_under_ncu_r2.err
 tail -3 gpurun_out/launches_r2.csv

@@ -40,8 +40,12 @@ elif what in ("lb1", "lb2"):
             ev.evaluate_device(what, d_in[k % 3].data_ptr(), M, best, d_out.data_ptr(), stream.cuda_stream)
         torch.cuda.synchronize()
 elif what == "rounds":
+    os.environ["TSB200_POOLS"] = "1"
     st = tsb200.nqueens_search_device(15, 1, 25, 50000, 1)  # 3 431 rounds in one launch of the persistent kernel
     assert (st.explored_tree, st.explored_sol) == (171129071, 2279184)
+elif what == "rounds17":  # four pools per launch (the default of the search driver), N = 17: 2 048 rounds per pool and launch
+    st = tsb200.nqueens_search_device(17, 1, 25, 50000, 1)
+    assert (st.explored_tree, st.explored_sol) == (8017021931, 95815104)
 elif what == "pool":
     st = tsb200.nqueens_search_device(17, 1, 25, 1 << 22, 1)  # 1 922 two-kernel rounds of up to 4 Mi parents
     assert (st.explored_tree, st.explored_sol) == (8017021931, 95815104)
