@@ -338,6 +338,9 @@ struct ExpandCtx {
     }
     if (!h_res) {
       TSB_CUDA(cudaHostAlloc(&h_res, sizeof(tsb::ExpandResult), cudaHostAllocPortable | cudaHostAllocMapped));
+      // (epochs start at 1: recycled pinned memory may hold another handle's old record, epoch included — the early
+      // wait below would take it for this handle's first round)
+      std::memset(h_res, 0, sizeof(tsb::ExpandResult));
       TSB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_res), h_res, 0));
     }
     if (tiles > tile_cap || side_bytes_per_tile > side_bytes) {
@@ -537,6 +540,7 @@ struct RoundsCtx {
     }
     if (!h_state) {
       TSB_CUDA(cudaHostAlloc(&h_state, sizeof(tsb::RoundsState), cudaHostAllocPortable | cudaHostAllocMapped));
+      std::memset(h_state, 0, sizeof(tsb::RoundsState));
       TSB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_state), h_state, 0));
     }
     return TSB_OK;

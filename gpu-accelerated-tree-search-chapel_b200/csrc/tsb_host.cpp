@@ -426,7 +426,7 @@ void nq_devpool_on(tsb_nq* h, int m, int M, Pool<tsb_nq_node>& pool, GpuTaskResu
 // Handles of the device-pool drivers are kept between searches (per device, N, g, M): a handle with its sibling
 // pools, arenas and fat arenas is ~1.4 GB of cudaMalloc / cudaFree per GPU, which at 8 GPUs cost more than the N = 17
 // search itself.  (The Chapel drivers declare their device arrays once, outside the search loop, as well.)
-// tsb_release_cached_handles frees them.
+// At most two idle handles are kept per device; tsb_release_cached_handles frees them all.
 struct NqHandleCache {
   struct Entry {
     int device, N, g, M;
@@ -455,8 +455,22 @@ struct NqHandleCache {
       tsb_nq_destroy(h);
       return;
     }
-    std::lock_guard<std::mutex> lk(mu);
-    idle.push_back({device, N, g, M, h});
+    // at most two idle handles per device (a handle with four pools holds ~1.4 GB): the oldest one goes
+    tsb_nq* evict = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      idle.push_back({device, N, g, M, h});
+      int on_device = 0;
+      for (const Entry& e : idle) on_device += e.device == device;
+      if (on_device > 2)
+        for (size_t i = 0; i < idle.size(); i++)
+          if (idle[i].device == device) {
+            evict = idle[i].h;
+            idle.erase(idle.begin() + static_cast<long>(i));
+            break;
+          }
+    }
+    if (evict) tsb_nq_destroy(evict);
   }
   void clear() {
     std::lock_guard<std::mutex> lk(mu);
