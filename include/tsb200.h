@@ -298,9 +298,12 @@ int tsb_nq_search(int N, int g, int m, int M, int D, tsb_search_stats* out);
 /* tsb_nq_search_device[_part] keep their handles (device pools, arenas) per (device, N, g, M) between calls; this
  * frees them.  TSB200_NO_HANDLE_CACHE=1: create and destroy per search. */
 void tsb_release_cached_handles(void);
-/* the same 3-step search with the pool(s) of step 2 resident on the device(s) (tsb_nq_pool_*): identical
- * chunk sequence, identical counts; the host only reads three counters per round.  D > 1 = the same static
- * strided split, one device pool per GPU; a task whose pool runs dry steals the oldest half of the fullest device
+/* the same 3-step search with the pool(s) of step 2 resident on the device(s) (tsb_nq_pool_*): identical counts; the
+ * host only reads three counters per call.  For chunks that fit the persistent kernel (M <= 56 832 on a B200) every
+ * task splits its pool once more (the same strided split) into 4 device pools that share every launch
+ * (tsb_nq_pool_run_multi): the chunk sequence is then the reference's for 4 D tasks; env TSB200_POOLS=1 = one pool
+ * per task = the reference's chunk sequence for D tasks.  D > 1 = the same static strided split over the GPUs; a
+ * task whose pools run dry steals the oldest half of the fullest device
  * pool over NVLink (the reference's intra-node work stealing, nqueens_multigpu_chpl.chpl:255-312, moved to the
  * device pools; env TSB200_NO_STEAL=1 = the static split alone). */
 int tsb_nq_search_device(int N, int g, int m, int M, int D, tsb_search_stats* out);
@@ -314,6 +317,9 @@ int tsb_nq_search_device_part(int N, int g, int m, int M, int D, int part, int d
 int tsb_pfsp_search(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out);
 /* the same with the pool(s) of step 2 resident on the device(s) (tsb_pfsp_pool_*) */
 int tsb_pfsp_search_device(int inst, int lb_kind, int ub, int m, int M, int D, tsb_search_stats* out);
+/* one task of the split (see tsb_nq_search_device_part).  The parts do not exchange their incumbent: with ub = 1 (the
+ * optimum is known up front) the parts' counts add up to the whole search's; with ub = 0 every part prunes with the
+ * best it finds itself, so the sum of the parts can exceed the single-process count (the optimum is still found). */
 int tsb_pfsp_search_device_part(int inst, int lb_kind, int ub, int m, int M, int D, int part, int device,
                                 tsb_search_stats* out);
 int tsb_pfsp_search_on(tsb_pfsp* h, int inst, int lb_kind, int ub, int m, int M, tsb_search_stats* out);

@@ -143,6 +143,18 @@ def test_search_on_a_precreated_handle(golden_dir):
             assert (st.explored_tree, st.explored_sol) == (nq["tree"], nq["sol"])
 
 
+def test_ta020_lb1d_search_has_the_chapel_program_count(golden_dir):
+    """ta020 with lb1_d is where the Chapel program (min_heads of Bound_simple.chpl) and the C baseline explore
+    different trees (836 490 312 against 859 257 178 nodes): the device-pool search matches the count of the reference's C
+    code rebuilt with the Chapel statement (tests/golden/make_golden_chapel.py)"""
+    gold = json.load(open(os.path.join(golden_dir, "pfsp_chapel_heads.json")))["counts"].get("ta020_lb1d")
+    if not gold:
+        pytest.skip("golden count not generated (make_golden_chapel.py --no-ta020)")
+    with tsb200.PfspEvaluator(20, M=1 << 20) as ev:
+        st = ev.search(20, "lb1_d", 1, 25, 1 << 20)
+    assert (st.explored_tree, st.explored_sol, st.best) == (gold["tree"], gold["sol"], gold["best"])
+
+
 def test_pool_compaction_and_growth(monkeypatch):
     monkeypatch.setenv("TSB200_POOL_CAP", "4000")
     st = tsb200.pfsp_search_device(14, "lb1", 1, 25, 400, 1)
