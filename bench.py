@@ -684,8 +684,10 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                              "frac": achieved / (peak * world), "peak_source": peak_src,
                              "traffic": None,
-                             "traffic_note": "profiles/nq_rounds_r2_ncu.txt (the N=15 search, 171 M nodes, in one launch): "
-                                             "0.75 MB read + 4.8 MB written in DRAM — a 2 MB round lives in the 126 MB L2",
+                             "traffic_note": "profiles/nq_rounds_pools_r2_ncu.txt (first launch of this search: 2 048 rounds of each "
+                                             "of the four pools, ~0.4 G nodes = 17 GB algorithmic): 98 MB read + 313 MB written "
+                                             "in DRAM — a 2 MB round lives in the 126 MB L2; profiles/nq_rounds_r2_ncu.txt (one "
+                                             "pool, the whole N=15 search in one launch): 0.75 MB read + 4.8 MB written",
                              "kernel": "nq_rounds_ll_kernel<17> (persistent, cooperative; four independent pools per "
                                        "launch, 74 CTAs each, two CTAs per SM)",
                              "bytes_per_launch": h["nodes"] / h["steps"] * NODE_BYTES, "kernel_us": kernel_s * 1e6,
