@@ -488,9 +488,9 @@ struct RoundsCtx {
   unsigned epoch = 0;
   bool attr_set = false;
   int threads = 256;  // CTA size (env TSB200_ROUNDS_THREADS = 256 | 512)
-  int ctas = 0;       // grid size (env TSB200_ROUNDS_CTAS; 0 = two CTAs per three SMs: an all-to-all flag exchange
-                      // among 148 CTAs costs 2-3x one among 74 (tools/flag_exchange.py), the per-CTA work grows
-                      // the other way; measured best around 100 CTAs of 256 threads)
+  int ctas = 0;       // CTAs per pool (env TSB200_ROUNDS_CTAS; 0 = nq_ll_grid's measured defaults: an all-to-all flag
+                      // exchange among 148 CTAs costs 2-3x one among 74 (tools/flag_exchange.py), the per-CTA work
+                      // grows the other way)
   int occ = 2;        // env TSB200_ROUNDS_OCC=3: three CTAs per SM (several pools per launch)
   int ppt = 0;        // env TSB200_ROUNDS_PPT=3: the 768-parent slices also where 512 would do (experiments)
   int version = 3;    // 3 = the fence-free kernel on the fat arena (nq_rounds_ll.cuh); 2 = nq_rounds.cuh (env TSB200_ROUNDS_V)
