@@ -287,7 +287,7 @@ typedef struct {
   double t_step1, t_step2, t_step3; /* seconds */
   uint64_t offloads, offloaded_parents, kernel_launches;
   uint64_t per_gpu_tree[8];
-  uint64_t steals;                /* successful steals between device pools (D > 1, one process) */
+  uint64_t steals;                /* successful steals between TASKS (D > 1, one process); moves between the pools of one task are not counted */
 } tsb_search_stats;
 
 /* step 1 of the drivers alone (nqueens_gpu_chpl.chpl:169-175): breadth-first from the root until the pool holds
